@@ -1,0 +1,850 @@
+// Exact flat (squared-L2) index on B200: bf16 tensor-core scan with shared-threshold candidate
+// filtering, exact fp32 re-rank with a provable error bound, exact fp32 fallback scan.
+//
+// Replaces faiss.IndexFlatL2 as used by the reference (eval/utils/get_index_faiss.py:58,
+// eval/eval_faiss.py:147-148,211).  Ranking score  s(q,x) = q.x - 0.5|x|^2  (argmax s == argmin
+// |q-x|^2), distance reported as |q|^2 - 2 s.
+//
+// One scan pass handles up to 256 query rows against the whole database:
+//   flat_prep_kernel    fp32 queries -> bf16 B-operand tile, |q|^2, pass state reset
+//   flat_scan_kernel    persistent, one CTA per SM, each CTA owns a contiguous run of 128-row DB
+//                       tiles: TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (M=128 DB rows,
+//                       N=queries, K=128, bf16, fp32 accumulators double-buffered in TMEM) ->
+//                       epilogue warps tcgen05.ld the accumulators, subtract 0.5|x|^2 and keep
+//                       only scores above a per-query threshold that all CTAs share through L2
+//                       (the kg-th largest of the per-CTA running maxima -- a valid lower bound on
+//                       the kg-th best score, maintained by one reducer warp per CTA, lock-free).
+//   flat_select_kernel  per query: gather survivors, exact fp32 re-score, sort, and PROVE the
+//                       top-k: every dropped row has bf16 score <= T, hence exact score <= T + eps
+//                       with eps = (2u+u^2)|q|max|x| (u = 2^-8); if the k-th exact score is not
+//                       above that, the query is handed to the fallback.
+//   flat_brute_*        exact fp32 CUDA-core scan for flagged queries / tiny databases.
+#include <cfloat>
+#include <climits>
+#include <cstring>
+
+#include "index.h"
+#include "ptx.cuh"
+
+namespace nafp {
+
+// ------------------------------------------------------------------------------------------
+// small kernels: row conversion at add(), query preparation
+// ------------------------------------------------------------------------------------------
+__global__ void flat_convert_rows_kernel(const float* __restrict__ x32, __nv_bfloat16* __restrict__ x16,
+                                         float* __restrict__ hn, int32_t* __restrict__ maxn2, int64_t row0,
+                                         int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    float mx = 0.f;
+    for (int64_t r = row0 + warp; r < row0 + n; r += nwarps) {
+        const float4 v = reinterpret_cast<const float4*>(x32 + r * D128)[lane];
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 packed;
+        packed.x = *reinterpret_cast<uint32_t*>(&a);
+        packed.y = *reinterpret_cast<uint32_t*>(&b);
+        reinterpret_cast<uint2*>(x16 + r * D128)[lane] = packed;
+        float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) hn[r] = 0.5f * ss;
+        mx = fmaxf(mx, ss);
+    }
+    if (lane == 0 && mx > 0.f) atomicMax(maxn2, __float_as_int(mx));
+}
+
+__global__ void flat_fill_kernel(float* hn, int64_t from, int64_t to, float v) {
+    int64_t i = from + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < to) hn[i] = v;
+}
+
+// one warp per query row of the pass (rows >= nq are zero padding)
+__global__ void flat_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, int grid_scan, int brute,
+                                 __nv_bfloat16* __restrict__ qbf, float* __restrict__ q32,
+                                 float* __restrict__ qn2, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg,
+                                 int32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nq_pad) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nq) v = reinterpret_cast<const float4*>(q + static_cast<int64_t>(row) * D128)[lane];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 packed;
+    packed.x = *reinterpret_cast<uint32_t*>(&a);
+    packed.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(qbf + row * D128)[lane] = packed;
+    reinterpret_cast<float4*>(q32 + row * D128)[lane] = v;
+    float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+        qn2[row] = ss;
+        Tg[row] = INT_MIN;
+        flags[row] = brute ? 1 : 0;
+    }
+    for (int g = lane; g < grid_scan; g += 32) Mx[row * grid_scan + g] = INT_MIN;
+}
+
+// ------------------------------------------------------------------------------------------
+// the scan
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_STAGES = 4;
+constexpr int SCAN_THREADS = 224;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue, warp 6 reducer
+constexpr int STAGE_BYTES = TILE_ROWS * D128 * 2;          // 32 KB: two 64-column K blocks of 16 KB
+constexpr int KBLOCK_BYTES = TILE_ROWS * 128;              // 16 KB
+constexpr int Q_BYTES_MAX = NQ_MAX * D128 * 2;             // 64 KB
+constexpr int SCAN_SMEM = Q_BYTES_MAX + SCAN_STAGES * STAGE_BYTES + 3 * NQ_MAX * 4 + 256 + 1024;
+constexpr int NEG_INF_ORD = static_cast<int>(0x807FFFFFu);  // f2ord(-inf)
+
+struct ScanBars {
+    uint64_t full[SCAN_STAGES];
+    uint64_t empty[SCAN_STAGES];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint64_t qfull;
+    uint32_t tmem_base;
+    int done;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                 const float* __restrict__ hn, int64_t n_search, int n_tiles, int nq_pad, int kg, int defer,
+                 int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
+                 int32_t* __restrict__ cnt, int32_t* __restrict__ flags) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_s = smem;                                   // [2][nq_pad][128 B]
+    uint8_t* a_s = smem + Q_BYTES_MAX;                     // [stage][2][128][128 B]
+    float* thr_s = reinterpret_cast<float*>(a_s + SCAN_STAGES * STAGE_BYTES);
+    int* lmax_s = reinterpret_cast<int*>(thr_s + NQ_MAX);
+    int* cnt_s = lmax_s + NQ_MAX;
+    ScanBars* bars = reinterpret_cast<ScanBars*>(cnt_s + NQ_MAX);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int G = gridDim.x;
+    const int cta = blockIdx.x;
+    const int per = n_tiles / G, rem = n_tiles % G;
+    const int t0 = cta * per + min(cta, rem);
+    const int n_own = per + (cta < rem ? 1 : 0);
+    const int dfr = min(defer, n_own);
+    const int n_iter = n_own + dfr;      // first dfr tiles: max-only pass, re-scanned normally at the end
+
+    for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
+        thr_s[i] = -INFINITY;
+        lmax_s[i] = INT_MIN;
+        cnt_s[i] = 0;
+    }
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_db);
+        for (int s = 0; s < SCAN_STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->tfull[a], 1);
+            mbar_init(&bars->tempty[a], 4);
+        }
+        mbar_init(&bars->qfull, 1);
+        bars->done = 0;
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars->qfull, 2u * nq_pad * 128u);
+            for (int kb = 0; kb < 2; ++kb)
+                for (int r0 = 0; r0 < nq_pad; r0 += 32)
+                    tma_load_2d(q_s + kb * (nq_pad * 128) + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
+            for (int i = 0; i < n_iter; ++i) {
+                const int s = i % SCAN_STAGES;
+                const uint32_t ph = (i / SCAN_STAGES) & 1;
+                mbar_wait(&bars->empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
+                const int tile = t0 + (i < n_own ? i : i - n_own);
+                uint8_t* dst = a_s + s * STAGE_BYTES;
+                tma_load_2d(dst, &tmap_db, &bars->full[s], 0, tile * TILE_ROWS);
+                tma_load_2d(dst + KBLOCK_BYTES, &tmap_db, &bars->full[s], 64, tile * TILE_ROWS);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(1u, TILE_ROWS, static_cast<uint32_t>(nq_pad));
+            const uint32_t q_addr = smem_u32(q_s);
+            const uint32_t a_addr = smem_u32(a_s);
+            mbar_wait(&bars->qfull, 0);
+            for (int i = 0; i < n_iter; ++i) {
+                const int s = i % SCAN_STAGES;
+                const uint32_t ph = (i / SCAN_STAGES) & 1;
+                const int acc = i & 1;
+                const uint32_t aph = (i >> 1) & 1;
+                mbar_wait(&bars->tempty[acc], aph ^ 1);
+                mbar_wait(&bars->full[s], ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * NQ_MAX;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t adesc = umma_desc_sw128(a_addr + s * STAGE_BYTES + kb * KBLOCK_BYTES + j * 32);
+                        const uint64_t bdesc = umma_desc_sw128(q_addr + kb * (nq_pad * 128) + j * 32);
+                        tc_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | j) != 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(&bars->empty[s]);
+                tc_commit(&bars->tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ------------------------------------------------------------ epilogue (4 warps)
+        const int qd = warp & 3;          // TMEM lane quadrant this warp may read
+        const int e = warp - 2;           // 0..3: share of the per-tile threshold bookkeeping
+        int pub[2] = {INT_MIN, INT_MIN};
+        int thr_ord[2] = {NEG_INF_ORD, NEG_INF_ORD};
+        uint64_t* my_pool = pool + static_cast<int64_t>(cta) * NQ_MAX * POOL_CAP;
+        for (int i = 0; i < n_iter; ++i) {
+            const int acc = i & 1;
+            const uint32_t aph = (i >> 1) & 1;
+            const int tile = t0 + (i < n_own ? i : i - n_own);
+            const uint32_t row = static_cast<uint32_t>(tile) * TILE_ROWS + qd * 32 + lane;
+            const float h = row < n_search ? __ldg(hn + row) : INFINITY;   // halo / padding rows never score
+            const bool maxonly = i < dfr;
+            mbar_wait(&bars->tfull[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * NQ_MAX;
+            for (int c0 = 0; c0 < nq_pad; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c0, v);
+                tc_wait_ld();
+                if (maxonly) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]) - h;
+                        const int m = __reduce_max_sync(0xffffffffu, f2ord(s));
+                        if (lane == j) atomicMax(&lmax_s[c0 + j], m);
+                    }
+                } else {
+                    bool anyp = false;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) anyp |= (__uint_as_float(v[j]) - h) > thr_s[c0 + j];
+                    if (__any_sync(0xffffffffu, anyp)) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(v[j]) - h;
+                            if (s > thr_s[c0 + j]) {
+                                const int so = f2ord(s);
+                                const int pos = atomicAdd(&cnt_s[c0 + j], 1);
+                                if (pos < POOL_CAP)
+                                    my_pool[(c0 + j) * POOL_CAP + pos] =
+                                        (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
+                                atomicMax(&lmax_s[c0 + j], so);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+            // publish this CTA's running maxima, pick up the shared thresholds
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int q = e * 64 + t * 32 + lane;
+                if (q < nq_pad) {
+                    const int m = *reinterpret_cast<volatile int*>(&lmax_s[q]);
+                    if (m > pub[t]) {
+                        st_relaxed(&Mx[q * G + cta], m);
+                        pub[t] = m;
+                    }
+                    const int tg = ld_relaxed(&Tg[q]);
+                    if (tg > thr_ord[t]) {
+                        thr_ord[t] = tg;
+                        thr_s[q] = ord2f(tg);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // all four epilogue warps are done appending before counts are published
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int q = e * 64 + t * 32 + lane;
+            if (q < nq_pad) {
+                const int c = cnt_s[q];
+                cnt[cta * NQ_MAX + q] = min(c, POOL_CAP);
+                if (c > POOL_CAP) flags[q] = 1;      // pool overflow -> exact fallback answers this query
+            }
+        }
+        if (lane == 0) atomicAdd(&bars->done, 1);
+    } else {
+        // ------------------------------------------------------------ threshold reducer (warp 6)
+        // For the queries assigned to this CTA: T = kg-th largest of the per-CTA maxima.  At least kg
+        // distinct rows score >= T, so dropping rows that score <= T can never lose a top-kg row.
+        while (*reinterpret_cast<volatile int*>(&bars->done) < 4) {
+            for (int q = cta; q < nq_pad; q += G) {
+                uint32_t u[5];
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const int g = lane + 32 * t;
+                    const int m = g < G ? ld_relaxed(&Mx[q * G + g]) : INT_MIN;
+                    u[t] = static_cast<uint32_t>(m) ^ 0x80000000u;
+                }
+                uint32_t res = 0;
+                for (int bit = 31; bit >= 0; --bit) {
+                    const uint32_t cand = res | (1u << bit);
+                    int c = 0;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) c += (u[t] >= cand) ? 1 : 0;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (c >= kg) res = cand;
+                }
+                const int T = static_cast<int>(res ^ 0x80000000u);
+                if (lane == 0 && T > NEG_INF_ORD && T > ld_relaxed(&Tg[q])) st_relaxed(&Tg[q], T);
+            }
+            __nanosleep(200);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// survivors -> exact fp32 re-rank + proof
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t score_key(float s, uint32_t row) {
+    return (static_cast<uint64_t>(static_cast<uint32_t>(f2ord(s)) ^ 0x80000000u) << 32) | (0xFFFFFFFFu - row);
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+    return ord2f(static_cast<int>(static_cast<uint32_t>(key >> 32) ^ 0x80000000u));
+}
+__device__ __forceinline__ uint32_t key_row(uint64_t key) { return 0xFFFFFFFFu - static_cast<uint32_t>(key); }
+
+// descending bitonic sort of n (power of two) keys in shared memory
+__device__ void bitonic_sort_desc(uint64_t* keys, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __restrict__ q32,
+                   const float* __restrict__ qn2, const float* __restrict__ x32, const float* __restrict__ hn,
+                   const int32_t* __restrict__ maxn2, const int32_t* __restrict__ Tg,
+                   const uint64_t* __restrict__ pool, const int32_t* __restrict__ cnt, int32_t* __restrict__ flags,
+                   int64_t label_offset, float* __restrict__ D, int64_t* __restrict__ I,
+                   unsigned long long* __restrict__ stats) {
+    __shared__ uint64_t keys[SELECT_CAP];
+    __shared__ int total_s;
+    const int q = blockIdx.x;
+    if (flags[q] != 0) return;
+    if (threadIdx.x == 0) total_s = 0;
+    __syncthreads();
+    bool over = false;
+    for (int g = threadIdx.x; g < grid_scan; g += blockDim.x) {
+        const int c = cnt[g * NQ_MAX + q];
+        if (c > 0) {
+            const int base = atomicAdd(&total_s, c);
+            if (base + c <= SELECT_CAP) {
+                const uint64_t* src = pool + (static_cast<int64_t>(g) * NQ_MAX + q) * POOL_CAP;
+                for (int i = 0; i < c; ++i) keys[base + i] = src[i];
+            } else {
+                over = true;
+            }
+        }
+    }
+    if (__syncthreads_or(over ? 1 : 0)) {
+        if (threadIdx.x == 0) flags[q] = 1;
+        return;
+    }
+    const int total = total_s;
+    const int64_t need = n_rows < k ? n_rows : k;
+    if (total < need) {
+        if (threadIdx.x == 0) flags[q] = 1;
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 qv = reinterpret_cast<const float4*>(q32 + q * D128)[lane];
+    for (int i = warp; i < total; i += 8) {
+        const uint32_t row = static_cast<uint32_t>(keys[i]);
+        const float s = warp_dot128(qv, x32 + static_cast<int64_t>(row) * D128, lane) - hn[row];
+        __syncwarp();
+        if (lane == 0) keys[i] = score_key(s, row);
+    }
+    int npow = 1;
+    while (npow < total) npow <<= 1;
+    __syncthreads();
+    for (int i = total + threadIdx.x; i < npow; i += blockDim.x) keys[i] = 0;
+    __syncthreads();
+    bitonic_sort_desc(keys, npow);
+    // proof: every row that is not a survivor has bf16 score <= T, hence exact score <= T + eps
+    const int tgo = Tg[q];
+    if (tgo > NEG_INF_ORD) {
+        const float qn = sqrtf(qn2[q]);
+        const float xn = sqrtf(__int_as_float(*maxn2));
+        const float u = 0.00390625f;
+        const float eps = (2.f * u + u * u) * qn * xn * 1.01f + 1e-5f * qn * xn + 1e-30f;
+        const float bound = ord2f(tgo) + eps;
+        const float sk = key_score(keys[need - 1]);
+        if (!(sk > bound)) {
+            if (threadIdx.x == 0) flags[q] = 2;
+            return;
+        }
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        if (j < need) {
+            const uint64_t key = keys[j];
+            D[static_cast<int64_t>(q) * k + j] = fmaxf(qn2[q] - 2.f * key_score(key), 0.f);
+            I[static_cast<int64_t>(q) * k + j] = static_cast<int64_t>(key_row(key)) + label_offset;
+        } else {
+            D[static_cast<int64_t>(q) * k + j] = INFINITY;
+            I[static_cast<int64_t>(q) * k + j] = -1;
+        }
+    }
+    if (threadIdx.x == 0) atomicAdd(&stats[3], static_cast<unsigned long long>(total));
+}
+
+// ------------------------------------------------------------------------------------------
+// exact fp32 fallback: flagged queries only
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flat_brute_scan_kernel(int k, int64_t n_rows, const float* __restrict__ q32, const float* __restrict__ x32,
+                       const float* __restrict__ hn, const int32_t* __restrict__ flags,
+                       uint64_t* __restrict__ part) {
+    __shared__ uint64_t lists[8][MAX_K];
+    const int q = blockIdx.y;
+    if (flags[q] == 0) return;
+    const int chunk = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t per = (n_rows + BRUTE_CHUNKS - 1) / BRUTE_CHUNKS;
+    const int64_t r0 = chunk * per;
+    const int64_t r1 = r0 + per < n_rows ? r0 + per : n_rows;
+    uint64_t* lst = lists[warp];
+    for (int i = lane; i < k; i += 32) lst[i] = 0;
+    __syncwarp();
+    const float4 qv = reinterpret_cast<const float4*>(q32 + q * D128)[lane];
+    uint64_t kth = 0;     // current k-th best key of this warp (0 = list not full)
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const float s = warp_dot128(qv, x32 + r * D128, lane) - hn[r];
+        const uint64_t key = score_key(s, static_cast<uint32_t>(r));
+        if (key > kth) {             // warp-uniform
+            if (lane == 0) {
+                int p = k - 1;
+                while (p > 0 && lst[p - 1] < key) {
+                    lst[p] = lst[p - 1];
+                    --p;
+                }
+                lst[p] = key;
+            }
+            __syncwarp();
+            kth = lst[k - 1];
+        }
+    }
+    __syncthreads();
+    // block merge: k rounds of arg-max over the 8 warp lists (each sorted descending)
+    if (warp == 0) {
+        uint64_t* out = part + (static_cast<int64_t>(q) * BRUTE_CHUNKS + chunk) * MAX_K;
+        int head = 0;     // lane w < 8 owns the read cursor of list w
+        for (int j = 0; j < k; ++j) {
+            uint64_t cand = (lane < 8 && head < k) ? lists[lane][head] : 0;
+            uint64_t best = cand;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane < 8 && cand == best && best != 0) ++head;   // keys are unique (row id inside)
+            if (lane == 0) out[j] = best;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+flat_brute_merge_kernel(int k, const float* __restrict__ qn2, const int32_t* __restrict__ flags,
+                        uint64_t* __restrict__ part, int64_t label_offset, float* __restrict__ D,
+                        int64_t* __restrict__ I, unsigned long long* __restrict__ stats) {
+    __shared__ uint64_t red[8];
+    __shared__ uint64_t winner;
+    const int q = blockIdx.x;
+    if (flags[q] == 0) return;
+    uint64_t* p = part + static_cast<int64_t>(q) * BRUTE_CHUNKS * MAX_K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = 0; j < k; ++j) {
+        uint64_t best = 0;
+        for (int c = threadIdx.x; c < BRUTE_CHUNKS * k; c += blockDim.x) {
+            const uint64_t v = p[(c / k) * MAX_K + (c % k)];
+            best = v > best ? v : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) red[warp] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t b = 0;
+            for (int w = 0; w < 8; ++w) b = red[w] > b ? red[w] : b;
+            winner = b;
+            if (b != 0) {
+                D[static_cast<int64_t>(q) * k + j] = fmaxf(qn2[q] - 2.f * key_score(b), 0.f);
+                I[static_cast<int64_t>(q) * k + j] = static_cast<int64_t>(key_row(b)) + label_offset;
+            } else {
+                D[static_cast<int64_t>(q) * k + j] = INFINITY;
+                I[static_cast<int64_t>(q) * k + j] = -1;
+            }
+        }
+        __syncthreads();
+        const uint64_t w = winner;
+        if (w != 0)
+            for (int c = threadIdx.x; c < BRUTE_CHUNKS * k; c += blockDim.x) {
+                uint64_t* slot = &p[(c / k) * MAX_K + (c % k)];
+                if (*slot == w) *slot = 0;
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+int index_reserve(nafp_index* idx, int64_t n_total) {
+    if (n_total <= idx->cap) return NAFP_OK;
+    nafp_ctx* ctx = idx->ctx;
+    const int64_t new_cap = round_up(n_total, TILE_ROWS);
+    float* x32 = nullptr;
+    __nv_bfloat16* x16 = nullptr;
+    float* hn = nullptr;
+    NAFP_CUDA(cudaMalloc(&x32, static_cast<size_t>(new_cap) * idx->d * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&x16, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16)));
+    NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap) * sizeof(float)));
+    NAFP_CUDA(cudaMemsetAsync(x16, 0, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16), ctx->stream));
+    if (idx->n > 0) {
+        NAFP_CUDA(cudaMemcpyAsync(x32, idx->x32, static_cast<size_t>(idx->n) * idx->d * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        NAFP_CUDA(cudaMemcpyAsync(x16, idx->x16, static_cast<size_t>(idx->n) * idx->d * sizeof(__nv_bfloat16),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        NAFP_CUDA(cudaMemcpyAsync(hn, idx->hn, static_cast<size_t>(idx->n) * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    {
+        const int64_t cnt = new_cap - idx->n;
+        const int threads = 256;
+        const int64_t blocks = (cnt + threads - 1) / threads;
+        flat_fill_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(hn, idx->n, new_cap, INFINITY);
+        ctx->launches++;
+        NAFP_CUDA(cudaGetLastError());
+    }
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (idx->x32) cudaFree(idx->x32);
+    if (idx->x16) cudaFree(idx->x16);
+    if (idx->hn) cudaFree(idx->hn);
+    idx->x32 = x32;
+    idx->x16 = x16;
+    idx->hn = hn;
+    idx->cap = new_cap;
+    // DB tensor map: [cap rows][128 bf16], box 64 columns x 128 rows, 128-byte swizzle
+    const uint64_t dims[2] = {static_cast<uint64_t>(idx->d), static_cast<uint64_t>(new_cap)};
+    const uint64_t strides[2] = {2, static_cast<uint64_t>(idx->d) * 2};
+    const uint32_t box[2] = {64, TILE_ROWS};
+    NAFP_TRY(make_tensor_map(&idx->tmap_db, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x16, dims, strides, box, nullptr,
+                             CU_TENSOR_MAP_SWIZZLE_128B));
+    idx->tmap_db_valid = true;
+    return NAFP_OK;
+}
+
+int flat_add_dev(nafp_index* idx, const float* x, int64_t n, bool src_is_host) {
+    if (n == 0) return NAFP_OK;
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    if (idx->n + n > idx->cap) {
+        int64_t want = idx->cap * 2;
+        if (want < idx->n + n) want = idx->n + n;
+        NAFP_TRY(index_reserve(idx, want));
+    }
+    NAFP_CUDA(cudaMemcpyAsync(idx->x32 + idx->n * idx->d, x, static_cast<size_t>(n) * idx->d * sizeof(float),
+                              src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    const int threads = 256;
+    int64_t blocks = (n * 32 + threads - 1) / threads;
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    flat_convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(idx->x32, idx->x16, idx->hn,
+                                                                                        idx->maxn2, idx->n, n);
+    ctx->launches++;
+    NAFP_CUDA(cudaGetLastError());
+    if (src_is_host) NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    idx->n += n;
+    return NAFP_OK;
+}
+
+static int ensure_scratch(nafp_index* idx) {
+    if (idx->scratch_ready) return NAFP_OK;
+    nafp_ctx* ctx = idx->ctx;
+    idx->grid = ctx->sm_count;
+    NAFP_REQUIRE(idx->grid <= 160, NAFP_ERR_UNSUPPORTED, "flat scan: %d SMs (reducer handles <= 160)", idx->grid);
+    const int G = idx->grid;
+    NAFP_CUDA(cudaMalloc(&idx->qbf, NQ_MAX * D128 * sizeof(__nv_bfloat16)));
+    NAFP_CUDA(cudaMalloc(&idx->q32, NQ_MAX * D128 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&idx->qn2, NQ_MAX * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&idx->Mx, static_cast<size_t>(NQ_MAX) * G * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->Tg, NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->pool, static_cast<size_t>(G) * NQ_MAX * POOL_CAP * sizeof(uint64_t)));
+    NAFP_CUDA(cudaMalloc(&idx->cnt, static_cast<size_t>(G) * NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->flags, NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->brute_part, static_cast<size_t>(NQ_MAX) * BRUTE_CHUNKS * MAX_K * sizeof(uint64_t)));
+    NAFP_CUDA(cudaMalloc(&idx->stats, 4 * sizeof(unsigned long long)));
+    NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const uint64_t dims[2] = {static_cast<uint64_t>(D128), static_cast<uint64_t>(NQ_MAX)};
+    const uint64_t strides[2] = {2, static_cast<uint64_t>(D128) * 2};
+    const uint32_t box[2] = {64, 32};
+    NAFP_TRY(make_tensor_map(&idx->tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, idx->qbf, dims, strides, box, nullptr,
+                             CU_TENSOR_MAP_SWIZZLE_128B));
+    NAFP_CUDA(cudaFuncSetAttribute(flat_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+    idx->scratch_ready = true;
+    return NAFP_OK;
+}
+
+int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_REQUIRE(k >= 1 && k <= MAX_K, NAFP_ERR_INVALID, "search: k=%d outside [1,%d]", k, MAX_K);
+    NAFP_REQUIRE(idx->d == D128, NAFP_ERR_UNSUPPORTED, "search: d=%d (the tensor-core scan is built for d=128)", idx->d);
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    NAFP_TRY(ensure_scratch(idx));
+    if (nq == 0) return NAFP_OK;
+    const int64_t n_search = (idx->search_rows >= 0 && idx->search_rows < idx->n) ? idx->search_rows : idx->n;
+    const int64_t n_tiles64 = (n_search + TILE_ROWS - 1) / TILE_ROWS;
+    const int n_tiles = static_cast<int>(n_tiles64);
+    const int kg = k + 28;
+    const int grid_scan = n_tiles < idx->grid ? (n_tiles > 0 ? n_tiles : 1) : idx->grid;
+    const bool brute = (n_search < 8192) || (kg > grid_scan) || (k > 64);
+    unsigned long long passes = 0;
+    for (int64_t p0 = 0; p0 < nq; p0 += NQ_MAX) {
+        const int np = static_cast<int>(nq - p0 < NQ_MAX ? nq - p0 : NQ_MAX);
+        const int nq_pad = (np + 31) / 32 * 32;
+        const float* qp = q_dev + p0 * D128;
+        float* Dp = D_dev + p0 * k;
+        int64_t* Ip = I_dev + p0 * k;
+        flat_prep_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, ctx->stream>>>(qp, np, nq_pad, grid_scan, brute ? 1 : 0,
+                                                                             idx->qbf, idx->q32, idx->qn2, idx->Mx,
+                                                                             idx->Tg, idx->flags);
+        ctx->launches++;
+        if (!brute) {
+            flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(
+                idx->tmap_q, idx->tmap_db, idx->hn, n_search, n_tiles, nq_pad, kg, 2, idx->Mx, idx->Tg, idx->pool, idx->cnt,
+                idx->flags);
+            ctx->launches++;
+            flat_select_kernel<<<np, 256, 0, ctx->stream>>>(np, k, grid_scan, n_search, idx->q32, idx->qn2, idx->x32,
+                                                            idx->hn, idx->maxn2, idx->Tg, idx->pool, idx->cnt,
+                                                            idx->flags, idx->label_offset, Dp, Ip, idx->stats);
+            ctx->launches++;
+        }
+        flat_brute_scan_kernel<<<dim3(BRUTE_CHUNKS, np), 256, 0, ctx->stream>>>(k, n_search, idx->q32, idx->x32, idx->hn,
+                                                                                idx->flags, idx->brute_part);
+        flat_brute_merge_kernel<<<np, 256, 0, ctx->stream>>>(k, idx->qn2, idx->flags, idx->brute_part,
+                                                             idx->label_offset, Dp, Ip, idx->stats);
+        ctx->launches += 2;
+        ++passes;
+    }
+    NAFP_CUDA(cudaGetLastError());
+    idx->host_rows += nq;
+    idx->host_passes += static_cast<int64_t>(passes);
+    return NAFP_OK;
+}
+
+}  // namespace nafp
+
+using namespace nafp;
+
+extern "C" {
+
+int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int pq_nbits, nafp_index** out) {
+    NAFP_REQUIRE(ctx && out, NAFP_ERR_INVALID, "nafp_index_create: NULL argument");
+    *out = nullptr;
+    NAFP_REQUIRE(type == NAFP_INDEX_FLAT_L2 || type == NAFP_INDEX_IVFPQ, NAFP_ERR_UNSUPPORTED,
+                 "nafp_index_create: index type %d is outside the hot path (l2, ivfpq)", type);
+    NAFP_REQUIRE(d == D128, NAFP_ERR_UNSUPPORTED, "nafp_index_create: d=%d; only d=128 (MODEL.EMB_SZ) is built", d);
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    nafp_index* idx = new nafp_index();
+    idx->ctx = ctx;
+    idx->type = type;
+    idx->d = d;
+    if (cudaMalloc(&idx->maxn2, sizeof(int32_t)) != cudaSuccess ||
+        cudaMemsetAsync(idx->maxn2, 0, sizeof(int32_t), ctx->stream) != cudaSuccess) {
+        set_error("nafp_index_create: cudaMalloc failed");
+        delete idx;
+        return NAFP_ERR_CUDA;
+    }
+    if (type == NAFP_INDEX_IVFPQ) {
+        int s = ivfpq_create(idx, nlist, pq_m, pq_nbits);
+        if (s != NAFP_OK) {
+            cudaFree(idx->maxn2);
+            delete idx;
+            return s;
+        }
+    }
+    *out = idx;
+    return NAFP_OK;
+}
+
+int nafp_index_destroy(nafp_index* idx) {
+    if (!idx) return NAFP_OK;
+    cudaSetDevice(idx->ctx->device);
+    cudaStreamSynchronize(idx->ctx->stream);
+    if (idx->ivf) ivfpq_destroy(idx);
+    void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
+                    idx->pool, idx->cnt, idx->flags, idx->brute_part, idx->stats, idx->stage_q, idx->stage_D,
+                    idx->stage_I};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    delete idx;
+    return NAFP_OK;
+}
+
+int nafp_index_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
+    NAFP_REQUIRE(idx, NAFP_ERR_INVALID, "nafp_index_train: idx is NULL");
+    if (idx->type == NAFP_INDEX_FLAT_L2) return NAFP_OK;
+    NAFP_REQUIRE(x_host && n > 0, NAFP_ERR_INVALID, "nafp_index_train: empty training set");
+    return ivfpq_train(idx, x_host, n, seed);
+}
+
+int nafp_index_is_trained(nafp_index* idx);
+
+static int add_common(nafp_index* idx, const float* x, int64_t n, bool host) {
+    NAFP_REQUIRE(idx && (n == 0 || x) && n >= 0, NAFP_ERR_INVALID, "nafp_index_add: bad arguments");
+    NAFP_REQUIRE(idx->n + n < (1ll << 32), NAFP_ERR_UNSUPPORTED, "nafp_index_add: more than 2^32 rows per shard");
+    if (idx->type == NAFP_INDEX_IVFPQ)
+        NAFP_REQUIRE(nafp_index_is_trained(idx) == 1, NAFP_ERR_STATE, "nafp_index_add: IVFPQ index is not trained");
+    const int64_t row0 = idx->n;
+    NAFP_TRY(flat_add_dev(idx, x, n, host));
+    if (idx->type == NAFP_INDEX_IVFPQ) NAFP_TRY(ivfpq_add_rows(idx, row0, n));
+    return NAFP_OK;
+}
+int nafp_index_add(nafp_index* idx, const float* x_host, int64_t n) { return add_common(idx, x_host, n, true); }
+int nafp_index_add_dev(nafp_index* idx, const float* x_dev, int64_t n) { return add_common(idx, x_dev, n, false); }
+
+int nafp_index_reserve(nafp_index* idx, int64_t n_total) {
+    NAFP_REQUIRE(idx && n_total >= 0, NAFP_ERR_INVALID, "nafp_index_reserve: bad arguments");
+    NAFP_CUDA(cudaSetDevice(idx->ctx->device));
+    return index_reserve(idx, n_total);
+}
+
+int64_t nafp_index_ntotal(nafp_index* idx) { return idx ? idx->n : 0; }
+
+int nafp_index_set_nprobe(nafp_index* idx, int nprobe) {
+    NAFP_REQUIRE(idx && nprobe >= 1, NAFP_ERR_INVALID, "nafp_index_set_nprobe: bad arguments");
+    idx->nprobe = nprobe;
+    return NAFP_OK;
+}
+int nafp_index_set_search_rows(nafp_index* idx, int64_t n_rows) {
+    NAFP_REQUIRE(idx, NAFP_ERR_INVALID, "nafp_index_set_search_rows: idx is NULL");
+    idx->search_rows = n_rows;
+    return NAFP_OK;
+}
+int nafp_index_set_label_offset(nafp_index* idx, int64_t offset) {
+    NAFP_REQUIRE(idx, NAFP_ERR_INVALID, "nafp_index_set_label_offset: idx is NULL");
+    idx->label_offset = offset;
+    return NAFP_OK;
+}
+
+int nafp_index_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    NAFP_REQUIRE(idx && nq >= 0 && (nq == 0 || (q_dev && D_dev && I_dev)), NAFP_ERR_INVALID,
+                 "nafp_index_search_dev: bad arguments");
+    if (idx->type == NAFP_INDEX_IVFPQ) return ivfpq_search_dev(idx, q_dev, nq, k, D_dev, I_dev);
+    return flat_search_dev(idx, q_dev, nq, k, D_dev, I_dev);
+}
+
+int nafp_index_search(nafp_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
+    NAFP_REQUIRE(idx && nq >= 0 && (nq == 0 || (q_host && D_host && I_host)), NAFP_ERR_INVALID,
+                 "nafp_index_search: bad arguments");
+    NAFP_REQUIRE(k >= 1 && k <= MAX_K, NAFP_ERR_INVALID, "search: k=%d outside [1,%d]", k, MAX_K);
+    if (nq == 0) return NAFP_OK;
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    if (idx->stage_q_rows < nq) {
+        if (idx->stage_q) cudaFree(idx->stage_q);
+        idx->stage_q = nullptr;
+        idx->stage_q_rows = 0;
+        NAFP_CUDA(cudaMalloc(&idx->stage_q, static_cast<size_t>(nq) * idx->d * sizeof(float)));
+        idx->stage_q_rows = nq;
+    }
+    if (idx->stage_out_elems < nq * k) {
+        if (idx->stage_D) cudaFree(idx->stage_D);
+        if (idx->stage_I) cudaFree(idx->stage_I);
+        idx->stage_D = nullptr;
+        idx->stage_I = nullptr;
+        idx->stage_out_elems = 0;
+        NAFP_CUDA(cudaMalloc(&idx->stage_D, static_cast<size_t>(nq) * k * sizeof(float)));
+        NAFP_CUDA(cudaMalloc(&idx->stage_I, static_cast<size_t>(nq) * k * sizeof(int64_t)));
+        idx->stage_out_elems = nq * k;
+    }
+    NAFP_CUDA(cudaMemcpyAsync(idx->stage_q, q_host, static_cast<size_t>(nq) * idx->d * sizeof(float),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    NAFP_TRY(nafp_index_search_dev(idx, idx->stage_q, nq, k, idx->stage_D, idx->stage_I));
+    NAFP_CUDA(cudaMemcpyAsync(D_host, idx->stage_D, static_cast<size_t>(nq) * k * sizeof(float), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    NAFP_CUDA(cudaMemcpyAsync(I_host, idx->stage_I, static_cast<size_t>(nq) * k * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NAFP_OK;
+}
+
+int nafp_index_reconstruct_host(nafp_index* idx, int64_t i0, int64_t n, float* out_host) {
+    NAFP_REQUIRE(idx && out_host && i0 >= 0 && n >= 0 && i0 + n <= idx->n, NAFP_ERR_INVALID,
+                 "nafp_index_reconstruct_host: range [%lld, %lld) outside [0, %lld)", (long long)i0,
+                 (long long)(i0 + n), (long long)(idx ? idx->n : 0));
+    if (n == 0) return NAFP_OK;
+    NAFP_CUDA(cudaMemcpyAsync(out_host, idx->x32 + i0 * idx->d, static_cast<size_t>(n) * idx->d * sizeof(float),
+                              cudaMemcpyDeviceToHost, idx->ctx->stream));
+    NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
+    return NAFP_OK;
+}
+
+int nafp_index_last_search_stats(nafp_index* idx, int64_t* out4) {
+    NAFP_REQUIRE(idx && out4, NAFP_ERR_INVALID, "nafp_index_last_search_stats: bad arguments");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (!idx->stats) return NAFP_OK;
+    unsigned long long h[4];
+    NAFP_CUDA(cudaMemcpyAsync(h, idx->stats, sizeof(h), cudaMemcpyDeviceToHost, idx->ctx->stream));
+    NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, sizeof(h), idx->ctx->stream));
+    NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
+    for (int i = 0; i < 4; ++i) out4[i] = static_cast<int64_t>(h[i]);
+    out4[0] = idx->host_rows;
+    out4[2] = idx->host_passes;
+    idx->host_rows = idx->host_passes = 0;
+    return NAFP_OK;
+}
+
+}  // extern "C"
