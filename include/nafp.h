@@ -142,10 +142,18 @@ int nafp_index_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k
 /* index.reconstruct_n(i0, n) -> (n,d) float32 (the reference's fake_recon_index rows,
  * eval/eval_faiss.py:167-171, without touching dummy_db.mm on disk). FLAT_L2 only. */
 int nafp_index_reconstruct_host(nafp_index* idx, int64_t i0, int64_t n, float* out_host);
-/* statistics of the last search call: [0] query rows, [1] rows answered by the exact fp32
- * fallback scan (bf16 bound not provable or candidate pool overflow), [2] scan passes,
- * [3] candidates re-ranked in fp32. */
-int nafp_index_last_search_stats(nafp_index* idx, int64_t* out4);
+/* counters since the previous call of this function, out8[0..7]: [0] query rows, [1] rows answered
+ * by the exact fp32 fallback scan, [2] scan passes, [3] candidates re-ranked in fp32,
+ * [5] fallback rows due to candidate-pool overflow / small database, [6] fallback rows because
+ * the bf16 error bound could not prove the top-k, [4],[7] reserved. */
+int nafp_index_last_search_stats(nafp_index* idx, int64_t* out8);
+
+/* developer probe of the last flat scan pass (256 entries each): fallback flags, shared
+ * thresholds, survivors per query row */
+int nafp_index_debug_last_pass(nafp_index* idx, int32_t* flags256, float* thr256, int32_t* total256);
+/* developer probe: per-CTA survivor counts [grid][256] and the tile index at which each CTA first
+ * saw a shared threshold per query [grid][256] (-1 = never); the first call arms the probe */
+int nafp_index_debug_enable(nafp_index* idx, int32_t* cnt_out, int32_t* first_out, int32_t* grid_out);
 
 /* ------------------------------------------------------------------ sequence matcher
  * Replaces the body of the hot loop eval/eval_faiss.py:204-232 for a batch of test ids.

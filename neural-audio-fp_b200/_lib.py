@@ -74,6 +74,8 @@ _SIGS = {
     "nafp_index_search_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "nafp_index_reconstruct_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "nafp_index_last_search_stats": (c_int, [c_void_p, _i64p]),
+    "nafp_index_debug_last_pass": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nafp_index_debug_enable": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nafp_seq_match": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "nafp_seq_gather_dev": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]),
     "nafp_seq_cand_dev": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32,

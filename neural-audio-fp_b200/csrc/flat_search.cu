@@ -22,6 +22,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstring>
+#include <vector>
 
 #include "index.h"
 #include "ptx.cuh"
@@ -64,7 +65,8 @@ __global__ void flat_fill_kernel(float* hn, int64_t from, int64_t to, float v) {
 __global__ void flat_prep_kernel(const float* __restrict__ q, int nq, int nq_pad, int grid_scan, int brute,
                                  __nv_bfloat16* __restrict__ qbf, float* __restrict__ q32,
                                  float* __restrict__ qn2, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg,
-                                 int32_t* __restrict__ flags) {
+                                 int32_t* __restrict__ flags, int32_t* __restrict__ fb_list,
+                                 int32_t* __restrict__ fb_count) {
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= nq_pad) return;
@@ -84,6 +86,8 @@ __global__ void flat_prep_kernel(const float* __restrict__ q, int nq, int nq_pad
         qn2[row] = ss;
         Tg[row] = INT_MIN;
         flags[row] = brute ? 1 : 0;
+        if (brute && row < nq) fb_list[row] = row;
+        if (row == 0) *fb_count = brute ? nq : 0;
     }
     for (int g = lane; g < grid_scan; g += 32) Mx[row * grid_scan + g] = INT_MIN;
 }
@@ -92,12 +96,14 @@ __global__ void flat_prep_kernel(const float* __restrict__ q, int nq, int nq_pad
 // the scan
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_STAGES = 4;
-constexpr int SCAN_THREADS = 224;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue, warp 6 reducer
+constexpr int SCAN_THREADS = 352;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue, warp 10 reducer
+constexpr int EPI_WARPS = 8;
 constexpr int STAGE_BYTES = TILE_ROWS * D128 * 2;          // 32 KB: two 64-column K blocks of 16 KB
 constexpr int KBLOCK_BYTES = TILE_ROWS * 128;              // 16 KB
 constexpr int Q_BYTES_MAX = NQ_MAX * D128 * 2;             // 64 KB
-constexpr int SCAN_SMEM = Q_BYTES_MAX + SCAN_STAGES * STAGE_BYTES + 3 * NQ_MAX * 4 + 256 + 1024;
+constexpr int SCAN_SMEM = Q_BYTES_MAX + SCAN_STAGES * STAGE_BYTES + (EPI_WARPS + 2) * NQ_MAX * 4 + 256 + 1024;
 constexpr int NEG_INF_ORD = static_cast<int>(0x807FFFFFu);  // f2ord(-inf)
+constexpr int MAXONLY_CAP = 24;     // at most this many leading tiles are scanned max-only and re-scanned
 
 struct ScanBars {
     uint64_t full[SCAN_STAGES];
@@ -106,20 +112,47 @@ struct ScanBars {
     uint64_t tempty[2];
     uint64_t qfull;
     uint32_t tmem_base;
-    int done;
+    int done;          // epilogue warps that finished
+    int decided;       // epilogue warps that fixed their number of max-only tiles
+    int redo[EPI_WARPS];   // ... and that number, per epilogue warp
 };
+
+__device__ __forceinline__ void smem_red_max(int* p, int v) {
+    asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int smem_atom_inc(int* p) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
+}
+__device__ __forceinline__ int smem_ld_volatile(const int* p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// all four epilogue warps have fixed how many leading tiles they scanned max-only -> the maximum
+__device__ __forceinline__ int wait_redo_count(ScanBars* bars) {
+    uint32_t spins = 0;
+    while (smem_ld_volatile(&bars->decided) < EPI_WARPS) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+    }
+    int r = 0;
+    for (int w = 0; w < EPI_WARPS; ++w) r = max(r, smem_ld_volatile(&bars->redo[w]));
+    return r;
+}
 
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                 const float* __restrict__ hn, int64_t n_search, int n_tiles, int nq_pad, int kg, int defer,
+                 const float* __restrict__ hn, int64_t n_search, int n_tiles, int nq_pad, int kg,
                  int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
-                 int32_t* __restrict__ cnt, int32_t* __restrict__ flags) {
+                 int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_s = smem;                                   // [2][nq_pad][128 B]
     uint8_t* a_s = smem + Q_BYTES_MAX;                     // [stage][2][128][128 B]
-    float* thr_s = reinterpret_cast<float*>(a_s + SCAN_STAGES * STAGE_BYTES);
-    int* lmax_s = reinterpret_cast<int*>(thr_s + NQ_MAX);
+    float* thr_s = reinterpret_cast<float*>(a_s + SCAN_STAGES * STAGE_BYTES);   // [EPI_WARPS][NQ_MAX]
+    int* lmax_s = reinterpret_cast<int*>(thr_s + EPI_WARPS * NQ_MAX);
     int* cnt_s = lmax_s + NQ_MAX;
     ScanBars* bars = reinterpret_cast<ScanBars*>(cnt_s + NQ_MAX);
 
@@ -130,11 +163,12 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int per = n_tiles / G, rem = n_tiles % G;
     const int t0 = cta * per + min(cta, rem);
     const int n_own = per + (cta < rem ? 1 : 0);
-    const int dfr = min(defer, n_own);
-    const int n_iter = n_own + dfr;      // first dfr tiles: max-only pass, re-scanned normally at the end
+    // Iterations 0..n_own-1 visit the CTA's tiles once.  Each epilogue warp scans its rows of the
+    // first R_w tiles "max-only" (no shared threshold exists yet, so it only feeds the running
+    // maxima); iterations n_own..n_own+R-1 (R = max R_w) re-visit those tiles with the threshold.
 
+    for (int i = threadIdx.x; i < EPI_WARPS * NQ_MAX; i += blockDim.x) thr_s[i] = -INFINITY;
     for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
-        thr_s[i] = -INFINITY;
         lmax_s[i] = INT_MIN;
         cnt_s[i] = 0;
     }
@@ -147,10 +181,12 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tfull[a], 1);
-            mbar_init(&bars->tempty[a], 4);
+            mbar_init(&bars->tempty[a], EPI_WARPS);
         }
         mbar_init(&bars->qfull, 1);
         bars->done = 0;
+        bars->decided = 0;
+        for (int w = 0; w < EPI_WARPS; ++w) bars->redo[w] = 0;
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -169,6 +205,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int kb = 0; kb < 2; ++kb)
                 for (int r0 = 0; r0 < nq_pad; r0 += 32)
                     tma_load_2d(q_s + kb * (nq_pad * 128) + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
+            int n_iter = n_own;
             for (int i = 0; i < n_iter; ++i) {
                 const int s = i % SCAN_STAGES;
                 const uint32_t ph = (i / SCAN_STAGES) & 1;
@@ -178,6 +215,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 uint8_t* dst = a_s + s * STAGE_BYTES;
                 tma_load_2d(dst, &tmap_db, &bars->full[s], 0, tile * TILE_ROWS);
                 tma_load_2d(dst + KBLOCK_BYTES, &tmap_db, &bars->full[s], 64, tile * TILE_ROWS);
+                if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
             }
         }
         __syncwarp();
@@ -188,6 +226,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t q_addr = smem_u32(q_s);
             const uint32_t a_addr = smem_u32(a_s);
             mbar_wait(&bars->qfull, 0);
+            int n_iter = n_own;
             for (int i = 0; i < n_iter; ++i) {
                 const int s = i % SCAN_STAGES;
                 const uint32_t ph = (i / SCAN_STAGES) & 1;
@@ -208,52 +247,77 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 tc_commit(&bars->empty[s]);
                 tc_commit(&bars->tfull[acc]);
+                if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
-        // ------------------------------------------------------------ epilogue (4 warps)
-        const int qd = warp & 3;          // TMEM lane quadrant this warp may read
-        const int e = warp - 2;           // 0..3: share of the per-tile threshold bookkeeping
-        int pub[2] = {INT_MIN, INT_MIN};
-        int thr_ord[2] = {NEG_INF_ORD, NEG_INF_ORD};
+    } else if (warp < 2 + EPI_WARPS) {
+        // ------------------------------------------------------------ epilogue (8 warps)
+        // Warp e reads TMEM lane quadrant (warp & 3) -- its 32 DB rows of the tile -- and takes every
+        // other 32-query chunk (half = e >> 2), so two warps per SM sub-partition hide each other's
+        // tcgen05.ld latency.  Each warp keeps a private copy of the thresholds of its own chunks.
+        const int qd = warp & 3;
+        const int e = warp - 2;           // 0..7
+        const int half = e >> 2;
+        float* my_thr = thr_s + e * NQ_MAX;
+        int pub = INT_MIN;
+        int thr_ord[NQ_MAX / 64];
+#pragma unroll
+        for (int r = 0; r < NQ_MAX / 64; ++r) thr_ord[r] = NEG_INF_ORD;
         uint64_t* my_pool = pool + static_cast<int64_t>(cta) * NQ_MAX * POOL_CAP;
+        bool normal = false;      // warp-uniform: thresholds of all of this warp's queries are known
+        bool all_valid = false;
+        int my_redo = 0;
+        int n_iter = n_own;
         for (int i = 0; i < n_iter; ++i) {
             const int acc = i & 1;
             const uint32_t aph = (i >> 1) & 1;
-            const int tile = t0 + (i < n_own ? i : i - n_own);
+            const bool second_visit = i >= n_own;
+            const int tile = t0 + (second_visit ? i - n_own : i);
             const uint32_t row = static_cast<uint32_t>(tile) * TILE_ROWS + qd * 32 + lane;
             const float h = row < n_search ? __ldg(hn + row) : INFINITY;   // halo / padding rows never score
-            const bool maxonly = i < dfr;
+            if (!normal && ((i >= 1 && all_valid) || i >= MAXONLY_CAP)) {
+                normal = true;
+                my_redo = i;
+                if (lane == 0) {
+                    bars->redo[e] = i;
+                    __threadfence_block();
+                    smem_atom_inc(&bars->decided);
+                }
+            }
+            const bool maxonly = !normal;
+            const bool skip = second_visit && (i - n_own) >= my_redo;     // this warp already scanned it normally
             mbar_wait(&bars->tfull[acc], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * NQ_MAX;
-            for (int c0 = 0; c0 < nq_pad; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                tc_wait_ld();
-                if (maxonly) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]) - h;
-                        const int m = __reduce_max_sync(0xffffffffu, f2ord(s));
-                        if (lane == j) atomicMax(&lmax_s[c0 + j], m);
-                    }
-                } else {
-                    bool anyp = false;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) anyp |= (__uint_as_float(v[j]) - h) > thr_s[c0 + j];
-                    if (__any_sync(0xffffffffu, anyp)) {
+            if (!skip) {
+                for (int c0 = half * 32; c0 < nq_pad; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    tc_wait_ld();
+                    if (maxonly) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float s = __uint_as_float(v[j]) - h;
-                            if (s > thr_s[c0 + j]) {
-                                const int so = f2ord(s);
-                                const int pos = atomicAdd(&cnt_s[c0 + j], 1);
-                                if (pos < POOL_CAP)
-                                    my_pool[(c0 + j) * POOL_CAP + pos] =
-                                        (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
-                                atomicMax(&lmax_s[c0 + j], so);
+                            const int m = __reduce_max_sync(0xffffffffu, f2ord(s));
+                            if (lane == j) smem_red_max(&lmax_s[c0 + j], m);
+                        }
+                    } else {
+                        bool anyp = false;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) anyp |= (__uint_as_float(v[j]) - h) > my_thr[c0 + j];
+                        if (__any_sync(0xffffffffu, anyp)) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float s = __uint_as_float(v[j]) - h;
+                                if (s > my_thr[c0 + j]) {
+                                    const int so = f2ord(s);
+                                    const int pos = smem_atom_inc(&cnt_s[c0 + j]);
+                                    if (pos < POOL_CAP)
+                                        my_pool[(c0 + j) * POOL_CAP + pos] =
+                                            (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
+                                    smem_red_max(&lmax_s[c0 + j], so);
+                                }
                             }
                         }
                     }
@@ -262,42 +326,71 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tempty[acc]);
-            // publish this CTA's running maxima, pick up the shared thresholds
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int q = e * 64 + t * 32 + lane;
+            // publish this CTA's running maxima: warp e owns queries [32 e, 32 e + 32)
+            {
+                const int q = e * 32 + lane;
                 if (q < nq_pad) {
-                    const int m = *reinterpret_cast<volatile int*>(&lmax_s[q]);
-                    if (m > pub[t]) {
+                    const int m = smem_ld_volatile(&lmax_s[q]);
+                    if (m > pub) {
                         st_relaxed(&Mx[q * G + cta], m);
-                        pub[t] = m;
-                    }
-                    const int tg = ld_relaxed(&Tg[q]);
-                    if (tg > thr_ord[t]) {
-                        thr_ord[t] = tg;
-                        thr_s[q] = ord2f(tg);
+                        pub = m;
                     }
                 }
             }
+            // refresh the thresholds of this warp's chunks: every tile while they are young, then every 4th
+            if (i < 12 || (i & 3) == 0 || i == n_own - 1) {
+                int tg[NQ_MAX / 64];
+#pragma unroll
+                for (int r = 0; r < NQ_MAX / 64; ++r) {
+                    const int q = half * 32 + r * 64 + lane;
+                    tg[r] = q < nq_pad ? ld_relaxed(&Tg[q]) : INT_MAX;
+                }
+                bool valid = true;
+#pragma unroll
+                for (int r = 0; r < NQ_MAX / 64; ++r) {
+                    const int q = half * 32 + r * 64 + lane;
+                    if (q < nq_pad) {
+                        if (tg[r] > thr_ord[r]) {
+                            if (dbg_first && qd == 0 && thr_ord[r] == NEG_INF_ORD) dbg_first[cta * NQ_MAX + q] = i;
+                            thr_ord[r] = tg[r];
+                            my_thr[q] = ord2f(tg[r]);
+                        }
+                        valid = valid && (thr_ord[r] > NEG_INF_ORD);
+                    }
+                }
+                all_valid = __all_sync(0xffffffffu, valid);
+            }
+            __syncwarp();
+            if (i == n_own - 1) {
+                if (!normal) {       // thresholds never arrived: everything is re-scanned (tiny databases)
+                    normal = true;
+                    my_redo = n_own;
+                    if (lane == 0) {
+                        bars->redo[e] = n_own;
+                        __threadfence_block();
+                        smem_atom_inc(&bars->decided);
+                    }
+                }
+                n_iter = n_own + wait_redo_count(bars);
+            }
         }
         __syncwarp();
-        // all four epilogue warps are done appending before counts are published
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int q = e * 64 + t * 32 + lane;
+        // all epilogue warps are done appending before counts are published
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        {
+            const int q = e * 32 + lane;
             if (q < nq_pad) {
                 const int c = cnt_s[q];
                 cnt[cta * NQ_MAX + q] = min(c, POOL_CAP);
                 if (c > POOL_CAP) flags[q] = 1;      // pool overflow -> exact fallback answers this query
             }
         }
-        if (lane == 0) atomicAdd(&bars->done, 1);
+        if (lane == 0) smem_atom_inc(&bars->done);
     } else {
-        // ------------------------------------------------------------ threshold reducer (warp 6)
+        // ------------------------------------------------------------ threshold reducer (warp 10)
         // For the queries assigned to this CTA: T = kg-th largest of the per-CTA maxima.  At least kg
         // distinct rows score >= T, so dropping rows that score <= T can never lose a top-kg row.
-        while (*reinterpret_cast<volatile int*>(&bars->done) < 4) {
+        while (smem_ld_volatile(&bars->done) < EPI_WARPS) {
             for (int q = cta; q < nq_pad; q += G) {
                 uint32_t u[5];
 #pragma unroll
@@ -318,7 +411,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int T = static_cast<int>(res ^ 0x80000000u);
                 if (lane == 0 && T > NEG_INF_ORD && T > ld_relaxed(&Tg[q])) st_relaxed(&Tg[q], T);
             }
-            __nanosleep(200);
+            __nanosleep(100);
         }
     }
 
@@ -363,12 +456,16 @@ flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __
                    const float* __restrict__ qn2, const float* __restrict__ x32, const float* __restrict__ hn,
                    const int32_t* __restrict__ maxn2, const int32_t* __restrict__ Tg,
                    const uint64_t* __restrict__ pool, const int32_t* __restrict__ cnt, int32_t* __restrict__ flags,
+                   int32_t* __restrict__ fb_list, int32_t* __restrict__ fb_count,
                    int64_t label_offset, float* __restrict__ D, int64_t* __restrict__ I,
                    unsigned long long* __restrict__ stats) {
     __shared__ uint64_t keys[SELECT_CAP];
     __shared__ int total_s;
     const int q = blockIdx.x;
-    if (flags[q] != 0) return;
+    if (flags[q] != 0) {                 // pool overflow seen by the scan
+        if (threadIdx.x == 0) fb_list[atomicAdd(fb_count, 1)] = q;
+        return;
+    }
     if (threadIdx.x == 0) total_s = 0;
     __syncthreads();
     bool over = false;
@@ -385,22 +482,44 @@ flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __
         }
     }
     if (__syncthreads_or(over ? 1 : 0)) {
-        if (threadIdx.x == 0) flags[q] = 1;
+        if (threadIdx.x == 0) {
+            flags[q] = 1;
+            fb_list[atomicAdd(fb_count, 1)] = q;
+        }
         return;
     }
     const int total = total_s;
     const int64_t need = n_rows < k ? n_rows : k;
     if (total < need) {
-        if (threadIdx.x == 0) flags[q] = 1;
+        if (threadIdx.x == 0) {
+            flags[q] = 1;
+            fb_list[atomicAdd(fb_count, 1)] = q;
+        }
         return;
     }
+    // exact fp32 re-score: 8 lanes per survivor (16 dims each), 4 survivors per warp per round,
+    // so every lane has 4 independent 16-byte loads in flight
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float4 qv = reinterpret_cast<const float4*>(q32 + q * D128)[lane];
-    for (int i = warp; i < total; i += 8) {
-        const uint32_t row = static_cast<uint32_t>(keys[i]);
-        const float s = warp_dot128(qv, x32 + static_cast<int64_t>(row) * D128, lane) - hn[row];
+    const int sub = lane >> 3, l8 = lane & 7;
+    float4 qv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qv[c] = reinterpret_cast<const float4*>(q32 + q * D128 + l8 * 16)[c];
+    for (int i0 = warp * 4; i0 < total; i0 += 32) {
+        const int i = i0 + sub;
+        const bool ok = i < total;
+        const uint32_t row = ok ? static_cast<uint32_t>(keys[i]) : 0u;
+        const float4* xr = reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(row) * D128 + l8 * 16);
+        const float4 a0 = xr[0], a1 = xr[1], a2 = xr[2], a3 = xr[3];
+        const float hh = hn[row];
+        float s = a0.x * qv[0].x + a0.y * qv[0].y + a0.z * qv[0].z + a0.w * qv[0].w;
+        s += a1.x * qv[1].x + a1.y * qv[1].y + a1.z * qv[1].z + a1.w * qv[1].w;
+        s += a2.x * qv[2].x + a2.y * qv[2].y + a2.z * qv[2].z + a2.w * qv[2].w;
+        s += a3.x * qv[3].x + a3.y * qv[3].y + a3.z * qv[3].z + a3.w * qv[3].w;
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
         __syncwarp();
-        if (lane == 0) keys[i] = score_key(s, row);
+        if (ok && l8 == 0) keys[i] = score_key(s - hh, row);
     }
     int npow = 1;
     while (npow < total) npow <<= 1;
@@ -418,7 +537,10 @@ flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __
         const float bound = ord2f(tgo) + eps;
         const float sk = key_score(keys[need - 1]);
         if (!(sk > bound)) {
-            if (threadIdx.x == 0) flags[q] = 2;
+            if (threadIdx.x == 0) {
+                flags[q] = 2;
+                fb_list[atomicAdd(fb_count, 1)] = q;
+            }
             return;
         }
     }
@@ -440,11 +562,12 @@ flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 flat_brute_scan_kernel(int k, int64_t n_rows, const float* __restrict__ q32, const float* __restrict__ x32,
-                       const float* __restrict__ hn, const int32_t* __restrict__ flags,
-                       uint64_t* __restrict__ part) {
+                       const float* __restrict__ hn, const int32_t* __restrict__ fb_list,
+                       const int32_t* __restrict__ fb_count, uint64_t* __restrict__ part) {
     __shared__ uint64_t lists[8][MAX_K];
-    const int q = blockIdx.y;
-    if (flags[q] == 0) return;
+    const int n_fb = *fb_count;
+    for (int li = blockIdx.y; li < n_fb; li += gridDim.y) {
+    const int q = fb_list[li];
     const int chunk = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t per = (n_rows + BRUTE_CHUNKS - 1) / BRUTE_CHUNKS;
@@ -488,16 +611,20 @@ flat_brute_scan_kernel(int k, int64_t n_rows, const float* __restrict__ q32, con
             if (lane == 0) out[j] = best;
         }
     }
+    __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(256)
 flat_brute_merge_kernel(int k, const float* __restrict__ qn2, const int32_t* __restrict__ flags,
+                        const int32_t* __restrict__ fb_list, const int32_t* __restrict__ fb_count,
                         uint64_t* __restrict__ part, int64_t label_offset, float* __restrict__ D,
                         int64_t* __restrict__ I, unsigned long long* __restrict__ stats) {
     __shared__ uint64_t red[8];
     __shared__ uint64_t winner;
-    const int q = blockIdx.x;
-    if (flags[q] == 0) return;
+    const int n_fb = *fb_count;
+    for (int li = blockIdx.x; li < n_fb; li += gridDim.x) {
+    const int q = fb_list[li];
     uint64_t* p = part + static_cast<int64_t>(q) * BRUTE_CHUNKS * MAX_K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = 0; j < k; ++j) {
@@ -534,7 +661,12 @@ flat_brute_merge_kernel(int k, const float* __restrict__ qn2, const int32_t* __r
             }
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
+    if (threadIdx.x == 0) {
+        atomicAdd(&stats[1], 1ull);
+        atomicAdd(&stats[4 + (flags[q] & 3)], 1ull);   // [5] overflow/short/brute mode, [6] bound not provable
+    }
+    __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -624,9 +756,11 @@ static int ensure_scratch(nafp_index* idx) {
     NAFP_CUDA(cudaMalloc(&idx->pool, static_cast<size_t>(G) * NQ_MAX * POOL_CAP * sizeof(uint64_t)));
     NAFP_CUDA(cudaMalloc(&idx->cnt, static_cast<size_t>(G) * NQ_MAX * sizeof(int32_t)));
     NAFP_CUDA(cudaMalloc(&idx->flags, NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->fb_list, (NQ_MAX + 1) * sizeof(int32_t)));
+    idx->fb_count = idx->fb_list + NQ_MAX;
     NAFP_CUDA(cudaMalloc(&idx->brute_part, static_cast<size_t>(NQ_MAX) * BRUTE_CHUNKS * MAX_K * sizeof(uint64_t)));
-    NAFP_CUDA(cudaMalloc(&idx->stats, 4 * sizeof(unsigned long long)));
-    NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    NAFP_CUDA(cudaMalloc(&idx->stats, 8 * sizeof(unsigned long long)));
+    NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
     const uint64_t dims[2] = {static_cast<uint64_t>(D128), static_cast<uint64_t>(NQ_MAX)};
     const uint64_t strides[2] = {2, static_cast<uint64_t>(D128) * 2};
     const uint32_t box[2] = {64, 32};
@@ -659,22 +793,25 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
         int64_t* Ip = I_dev + p0 * k;
         flat_prep_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, ctx->stream>>>(qp, np, nq_pad, grid_scan, brute ? 1 : 0,
                                                                              idx->qbf, idx->q32, idx->qn2, idx->Mx,
-                                                                             idx->Tg, idx->flags);
+                                                                             idx->Tg, idx->flags, idx->fb_list, idx->fb_count);
         ctx->launches++;
         if (!brute) {
             flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(
-                idx->tmap_q, idx->tmap_db, idx->hn, n_search, n_tiles, nq_pad, kg, 2, idx->Mx, idx->Tg, idx->pool, idx->cnt,
-                idx->flags);
+                idx->tmap_q, idx->tmap_db, idx->hn, n_search, n_tiles, nq_pad, kg, idx->Mx, idx->Tg, idx->pool, idx->cnt,
+                idx->flags, idx->dbg_first);
             ctx->launches++;
             flat_select_kernel<<<np, 256, 0, ctx->stream>>>(np, k, grid_scan, n_search, idx->q32, idx->qn2, idx->x32,
                                                             idx->hn, idx->maxn2, idx->Tg, idx->pool, idx->cnt,
-                                                            idx->flags, idx->label_offset, Dp, Ip, idx->stats);
+                                                            idx->flags, idx->fb_list, idx->fb_count, idx->label_offset,
+                                                            Dp, Ip, idx->stats);
             ctx->launches++;
         }
-        flat_brute_scan_kernel<<<dim3(BRUTE_CHUNKS, np), 256, 0, ctx->stream>>>(k, n_search, idx->q32, idx->x32, idx->hn,
-                                                                                idx->flags, idx->brute_part);
-        flat_brute_merge_kernel<<<np, 256, 0, ctx->stream>>>(k, idx->qn2, idx->flags, idx->brute_part,
-                                                             idx->label_offset, Dp, Ip, idx->stats);
+        const int fb_slots = brute ? (np < 32 ? np : 32) : 4;
+        flat_brute_scan_kernel<<<dim3(BRUTE_CHUNKS, fb_slots), 256, 0, ctx->stream>>>(
+            k, n_search, idx->q32, idx->x32, idx->hn, idx->fb_list, idx->fb_count, idx->brute_part);
+        flat_brute_merge_kernel<<<fb_slots, 256, 0, ctx->stream>>>(k, idx->qn2, idx->flags, idx->fb_list, idx->fb_count,
+                                                                   idx->brute_part, idx->label_offset, Dp, Ip,
+                                                                   idx->stats);
         ctx->launches += 2;
         ++passes;
     }
@@ -725,7 +862,7 @@ int nafp_index_destroy(nafp_index* idx) {
     cudaStreamSynchronize(idx->ctx->stream);
     if (idx->ivf) ivfpq_destroy(idx);
     void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
-                    idx->pool, idx->cnt, idx->flags, idx->brute_part, idx->stats, idx->stage_q, idx->stage_D,
+                    idx->pool, idx->cnt, idx->flags, idx->fb_list, idx->brute_part, idx->stats, idx->dbg_first, idx->stage_q, idx->stage_D,
                     idx->stage_I};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -832,15 +969,54 @@ int nafp_index_reconstruct_host(nafp_index* idx, int64_t i0, int64_t n, float* o
     return NAFP_OK;
 }
 
+// developer probe: state of the last scan pass (flags, shared thresholds as float, survivors per query)
+int nafp_index_debug_enable(nafp_index* idx, int32_t* cnt_out, int32_t* first_out, int32_t* grid_out) {
+    // first call allocates the probe buffer; later calls copy cnt[grid][256] / first-threshold tile[grid][256]
+    NAFP_REQUIRE(idx && idx->scratch_ready, NAFP_ERR_STATE, "debug: search once first");
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t n = static_cast<size_t>(idx->grid) * NQ_MAX;
+    if (!idx->dbg_first) {
+        NAFP_CUDA(cudaMalloc(&idx->dbg_first, n * 4));
+        NAFP_CUDA(cudaMemset(idx->dbg_first, 0xFF, n * 4));
+    }
+    if (grid_out) *grid_out = idx->grid;
+    if (cnt_out) NAFP_CUDA(cudaMemcpy(cnt_out, idx->cnt, n * 4, cudaMemcpyDeviceToHost));
+    if (first_out) {
+        NAFP_CUDA(cudaMemcpy(first_out, idx->dbg_first, n * 4, cudaMemcpyDeviceToHost));
+        NAFP_CUDA(cudaMemset(idx->dbg_first, 0xFF, n * 4));
+    }
+    return NAFP_OK;
+}
+
+int nafp_index_debug_last_pass(nafp_index* idx, int32_t* flags256, float* thr256, int32_t* total256) {
+    NAFP_REQUIRE(idx && idx->scratch_ready && flags256 && thr256 && total256, NAFP_ERR_INVALID, "debug: bad arguments");
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> tg(NQ_MAX), cnt(static_cast<size_t>(idx->grid) * NQ_MAX);
+    NAFP_CUDA(cudaMemcpy(flags256, idx->flags, NQ_MAX * 4, cudaMemcpyDeviceToHost));
+    NAFP_CUDA(cudaMemcpy(tg.data(), idx->Tg, NQ_MAX * 4, cudaMemcpyDeviceToHost));
+    NAFP_CUDA(cudaMemcpy(cnt.data(), idx->cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < NQ_MAX; ++q) {
+        int32_t o = tg[q];
+        uint32_t b = static_cast<uint32_t>(o >= 0 ? o : (o ^ 0x7FFFFFFF));
+        memcpy(&thr256[q], &b, 4);
+        int64_t t = 0;
+        for (int g = 0; g < idx->grid; ++g) t += cnt[static_cast<size_t>(g) * NQ_MAX + q];
+        total256[q] = static_cast<int32_t>(t);
+    }
+    return NAFP_OK;
+}
+
 int nafp_index_last_search_stats(nafp_index* idx, int64_t* out4) {
     NAFP_REQUIRE(idx && out4, NAFP_ERR_INVALID, "nafp_index_last_search_stats: bad arguments");
-    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (int i = 0; i < 8; ++i) out4[i] = 0;
     if (!idx->stats) return NAFP_OK;
-    unsigned long long h[4];
+    unsigned long long h[8];
     NAFP_CUDA(cudaMemcpyAsync(h, idx->stats, sizeof(h), cudaMemcpyDeviceToHost, idx->ctx->stream));
     NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, sizeof(h), idx->ctx->stream));
     NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
-    for (int i = 0; i < 4; ++i) out4[i] = static_cast<int64_t>(h[i]);
+    for (int i = 0; i < 8; ++i) out4[i] = static_cast<int64_t>(h[i]);
     out4[0] = idx->host_rows;
     out4[2] = idx->host_passes;
     idx->host_rows = idx->host_passes = 0;

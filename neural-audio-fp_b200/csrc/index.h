@@ -46,8 +46,11 @@ struct nafp_index {
     uint64_t* pool = nullptr;         // [grid][NQ_MAX][POOL_CAP]
     int32_t* cnt = nullptr;           // [grid][NQ_MAX]
     int32_t* flags = nullptr;         // [NQ_MAX] != 0 -> answered by the exact fallback
+    int32_t* fb_list = nullptr;       // [NQ_MAX] query rows handed to the fallback, + count
+    int32_t* fb_count = nullptr;
     uint64_t* brute_part = nullptr;   // [NQ_MAX][BRUTE_CHUNKS][MAX_K]
-    unsigned long long* stats = nullptr;   // [4] device counters
+    unsigned long long* stats = nullptr;   // [8] device counters
+    int32_t* dbg_first = nullptr;     // developer probe: [grid][NQ_MAX] tile index of the first shared threshold
     // staging for the host entry points
     float* stage_q = nullptr;  int64_t stage_q_rows = 0;
     float* stage_D = nullptr;  int64_t* stage_I = nullptr;  int64_t stage_out_elems = 0;

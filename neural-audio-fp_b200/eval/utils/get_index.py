@@ -80,6 +80,11 @@ class Index:
     def add_dev(self, dev_ptr, n):
         check(lib.nafp_index_add_dev(self.h, ctypes.c_void_p(dev_ptr), int(n)))
 
+    def search_dev(self, q_dev_ptr, nq, k, D_dev_ptr, I_dev_ptr):
+        """Device-pointer search, asynchronous on the context stream."""
+        check(lib.nafp_index_search_dev(self.h, ctypes.c_void_p(q_dev_ptr), int(nq), int(k),
+                                        ctypes.c_void_p(D_dev_ptr), ctypes.c_void_p(I_dev_ptr)))
+
     def search(self, q, k):
         q = _f32c(q)
         if q.ndim != 2 or q.shape[1] != self.d:
@@ -103,9 +108,10 @@ class Index:
         check(lib.nafp_index_set_search_rows(self.h, int(n)))
 
     def last_search_stats(self):
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(8, dtype=np.int64)
         check(lib.nafp_index_last_search_stats(self.h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
-        return dict(rows=int(out[0]), fallback_rows=int(out[1]), passes=int(out[2]), reranked=int(out[3]))
+        return dict(rows=int(out[0]), fallback_rows=int(out[1]), passes=int(out[2]), reranked=int(out[3]),
+                    fallback_overflow=int(out[5]), fallback_bound=int(out[6]))
 
     def seq_match(self, query, test_ids, seq_lens, k_probe=20):
         """Batched body of the reference's evaluation loop (``eval/eval_faiss.py:204-232``).
