@@ -269,13 +269,29 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         bool all_valid = false;
         int my_redo = 0;
         int n_iter = n_own;
+        // 0.5|x|^2 of this thread's row, prefetched one tile ahead (it is a cold DRAM read every tile)
+        auto load_h = [&](int it) -> float {
+            const int tl = t0 + (it >= n_own ? it - n_own : it);
+            const uint32_t rw = static_cast<uint32_t>(tl) * TILE_ROWS + qd * 32 + lane;
+            return (tl < n_tiles && rw < n_search) ? __ldg(hn + rw) : INFINITY;   // halo / padding rows never score
+        };
+        float h_next = load_h(0);
         for (int i = 0; i < n_iter; ++i) {
             const int acc = i & 1;
             const uint32_t aph = (i >> 1) & 1;
             const bool second_visit = i >= n_own;
             const int tile = t0 + (second_visit ? i - n_own : i);
             const uint32_t row = static_cast<uint32_t>(tile) * TILE_ROWS + qd * 32 + lane;
-            const float h = row < n_search ? __ldg(hn + row) : INFINITY;   // halo / padding rows never score
+            const float h = h_next;
+            h_next = load_h(i + 1);
+            // shared thresholds of this warp's chunks: loads issued now, consumed after the tile
+            const bool refresh = i < 12 || (i & 3) == 0 || i == n_own - 1;
+            int tg[NQ_MAX / 64];
+#pragma unroll
+            for (int r = 0; r < NQ_MAX / 64; ++r) {
+                const int q = half * 32 + r * 64 + lane;
+                tg[r] = (refresh && q < nq_pad) ? ld_relaxed(&Tg[q]) : INT_MIN;
+            }
             if (!normal && ((i >= 1 && all_valid) || i >= MAXONLY_CAP)) {
                 normal = true;
                 my_redo = i;
@@ -304,8 +320,15 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         }
                     } else {
                         bool anyp = false;
+                        const float4* thr4 = reinterpret_cast<const float4*>(my_thr + c0);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) anyp |= (__uint_as_float(v[j]) - h) > my_thr[c0 + j];
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 t4 = thr4[j4];
+                            anyp |= (__uint_as_float(v[4 * j4 + 0]) - h) > t4.x;
+                            anyp |= (__uint_as_float(v[4 * j4 + 1]) - h) > t4.y;
+                            anyp |= (__uint_as_float(v[4 * j4 + 2]) - h) > t4.z;
+                            anyp |= (__uint_as_float(v[4 * j4 + 3]) - h) > t4.w;
+                        }
                         if (__any_sync(0xffffffffu, anyp)) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -337,14 +360,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     }
                 }
             }
-            // refresh the thresholds of this warp's chunks: every tile while they are young, then every 4th
-            if (i < 12 || (i & 3) == 0 || i == n_own - 1) {
-                int tg[NQ_MAX / 64];
-#pragma unroll
-                for (int r = 0; r < NQ_MAX / 64; ++r) {
-                    const int q = half * 32 + r * 64 + lane;
-                    tg[r] = q < nq_pad ? ld_relaxed(&Tg[q]) : INT_MAX;
-                }
+            // consume the threshold loads issued at the top of the iteration
+            if (refresh) {
                 bool valid = true;
 #pragma unroll
                 for (int r = 0; r < NQ_MAX / 64; ++r) {
