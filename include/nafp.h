@@ -65,6 +65,16 @@ int nafp_memcpy_d2h(nafp_ctx* ctx, void* dst_host, const void* src_dev, int64_t 
 int nafp_timer_start(nafp_ctx* ctx);
 int nafp_timer_stop(nafp_ctx* ctx, float* out_ms);
 
+/* ------------------------------------------------------------------ synthetic inputs
+ * Seeded, counter-based generators for the shapes BASELINE.json names (no datasets offline; the
+ * full-scale inputs are far too large to stage from the host).  Row / segment i depends only on
+ * (seed, i), so any shard regenerates its own slice.  Measurement and test infrastructure. */
+/* unit-norm 128-d rows with AR(1) correlation `rho` inside `track_len`-row tracks -> out_dev (n_rows,128) */
+int nafp_synth_fp_rows(nafp_ctx* ctx, int64_t seed, int64_t row0, int64_t n_rows, int32_t track_len,
+                       float rho, float* out_dev);
+/* one-second 8 kHz "music-like" segments -> out_dev (n_seg, 8000) float32 */
+int nafp_synth_audio(nafp_ctx* ctx, int64_t seed, int64_t seg0, int64_t n_seg, float* out_dev);
+
 /* ------------------------------------------------------------------ extractor
  * Replaces the native work behind `test_step(X, m_pre, m_fp)` (model/generate.py:83-88):
  * Melspec_layer.call (model/fp/melspec/melspectrogram.py:102-112) and FingerPrinter.call
@@ -147,6 +157,11 @@ int nafp_index_reconstruct_host(nafp_index* idx, int64_t i0, int64_t n, float* o
  * [5] fallback rows due to candidate-pool overflow / small database, [6] fallback rows because
  * the bf16 error bound could not prove the top-k, [4],[7] reserved. */
 int nafp_index_last_search_stats(nafp_index* idx, int64_t* out8);
+
+/* CUDA-event timing of the scan kernel alone, on the launching stream (bench roofline):
+ * enable != 0 arms it; every call returns and resets the summed duration / launch count since the
+ * previous call (at most 8192 launches are recorded between calls). */
+int nafp_index_profile_scans(nafp_index* idx, int enable, double* total_ms, int64_t* n_scans);
 
 /* developer probe of the last flat scan pass (256 entries each): fallback flags, shared
  * thresholds, survivors per query row */

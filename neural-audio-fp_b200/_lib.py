@@ -52,6 +52,8 @@ _SIGS = {
     "nafp_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
     "nafp_timer_start": (c_int, [c_void_p]),
     "nafp_timer_stop": (c_int, [c_void_p, _fp]),
+    "nafp_synth_fp_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_float, c_void_p]),
+    "nafp_synth_audio": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "nafp_weights_load": (c_int, [c_void_p, POINTER(_fp), POINTER(_fp), POINTER(_fp), POINTER(_fp), _fp, _fp, _fp, _fp]),
     "nafp_logmel_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "nafp_encoder_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -74,6 +76,7 @@ _SIGS = {
     "nafp_index_search_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "nafp_index_reconstruct_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "nafp_index_last_search_stats": (c_int, [c_void_p, _i64p]),
+    "nafp_index_profile_scans": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), _i64p]),
     "nafp_index_debug_last_pass": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nafp_index_debug_enable": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nafp_seq_match": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "flat_search.cu", "seq_match.cu", "ivfpq.cu", "logmel.cu", "encoder.cu"]
+SOURCES = ["capi.cu", "flat_search.cu", "seq_match.cu", "ivfpq.cu", "logmel.cu", "encoder.cu", "synth.cu"]
 OUT = os.path.join(HERE, "libnafp.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -689,6 +689,7 @@ flat_brute_merge_kernel(int k, const float* __restrict__ qn2, const int32_t* __r
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+constexpr int PROF_RING = 8192;
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 int index_reserve(nafp_index* idx, int64_t n_total) {
@@ -813,10 +814,16 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
                                                                              idx->Tg, idx->flags, idx->fb_list, idx->fb_count);
         ctx->launches++;
         if (!brute) {
+            const bool prof = idx->profile && idx->prof_n < PROF_RING;
+            if (prof) cudaEventRecord(idx->prof_ev[2 * idx->prof_n], ctx->stream);
             flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(
                 idx->tmap_q, idx->tmap_db, idx->hn, n_search, n_tiles, nq_pad, kg, idx->Mx, idx->Tg, idx->pool, idx->cnt,
                 idx->flags, idx->dbg_first);
             ctx->launches++;
+            if (prof) {
+                cudaEventRecord(idx->prof_ev[2 * idx->prof_n + 1], ctx->stream);
+                idx->prof_n++;
+            }
             flat_select_kernel<<<np, 256, 0, ctx->stream>>>(np, k, grid_scan, n_search, idx->q32, idx->qn2, idx->x32,
                                                             idx->hn, idx->maxn2, idx->Tg, idx->pool, idx->cnt,
                                                             idx->flags, idx->fb_list, idx->fb_count, idx->label_offset,
@@ -878,6 +885,7 @@ int nafp_index_destroy(nafp_index* idx) {
     cudaSetDevice(idx->ctx->device);
     cudaStreamSynchronize(idx->ctx->stream);
     if (idx->ivf) ivfpq_destroy(idx);
+    for (auto& e : idx->prof_ev) cudaEventDestroy(e);
     void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
                     idx->pool, idx->cnt, idx->flags, idx->fb_list, idx->brute_part, idx->stats, idx->dbg_first, idx->stage_q, idx->stage_D,
                     idx->stage_I};
@@ -1022,6 +1030,29 @@ int nafp_index_debug_last_pass(nafp_index* idx, int32_t* flags256, float* thr256
         for (int g = 0; g < idx->grid; ++g) t += cnt[static_cast<size_t>(g) * NQ_MAX + q];
         total256[q] = static_cast<int32_t>(t);
     }
+    return NAFP_OK;
+}
+
+int nafp_index_profile_scans(nafp_index* idx, int enable, double* total_ms, int64_t* n_scans) {
+    // enable != 0: start timing every scan-kernel launch with CUDA events on the ctx stream;
+    // then (any value): report and reset what was collected since the previous call
+    NAFP_REQUIRE(idx, NAFP_ERR_INVALID, "nafp_index_profile_scans: idx is NULL");
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (int64_t i = 0; i < idx->prof_n; ++i) {
+        float ms = 0.f;
+        NAFP_CUDA(cudaEventElapsedTime(&ms, idx->prof_ev[2 * i], idx->prof_ev[2 * i + 1]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (n_scans) *n_scans = idx->prof_n;
+    idx->prof_n = 0;
+    if (enable && idx->prof_ev.empty()) {
+        idx->prof_ev.resize(2 * PROF_RING);
+        for (auto& e : idx->prof_ev) NAFP_CUDA(cudaEventCreate(&e));
+    }
+    idx->profile = enable != 0;
     return NAFP_OK;
 }
 

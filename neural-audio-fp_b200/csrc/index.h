@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include <vector>
 
 namespace nafp {
 
@@ -56,6 +57,11 @@ struct nafp_index {
     float* stage_D = nullptr;  int64_t* stage_I = nullptr;  int64_t stage_out_elems = 0;
 
     int64_t host_rows = 0, host_passes = 0;   // since the last nafp_index_last_search_stats
+
+    // optional CUDA-event timing of every scan launch (bench roofline): ring of event pairs
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;     // [2 * PROF_RING]
+    int64_t prof_n = 0;
 
     int nprobe = 1;
     nafp::IvfPq* ivf = nullptr;

@@ -1,0 +1,199 @@
+"""Row-sharded database across the GPUs of one node (SURVEY §8 e).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink).  The database [dummy_db; db] is split
+into contiguous row blocks; rank r additionally keeps a copy of the ``halo`` rows that follow its
+block (max sequence length - 1), so every candidate sequence that STARTS in its block can be scored
+locally.  Queries are replicated.  Per batch of test ids:
+
+    local top-k per query row  ->  all-gather (W, rows, k)  ->  merge to the global top-k
+    ->  every rank scores the candidates it owns (-inf elsewhere)  ->  max all-reduce  ->  top-10
+
+The two collectives move k*12 bytes per query row per rank and 4 bytes per candidate score; they are
+the only exchange steps of the path.  The orchestration below is backend-agnostic (``ops`` does the
+local work, ``comm`` the collectives) so that the host logic is testable with gloo on CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+SEQ_MAXC = 1024
+N_PRED = 10
+
+
+def shard_bounds(n_total, rank, world):
+    """Contiguous, balanced row block [lo, hi) of rank ``rank``."""
+    per, rem = divmod(int(n_total), int(world))
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def shard_with_halo(n_total, rank, world, halo):
+    lo, hi = shard_bounds(n_total, rank, world)
+    return lo, hi, min(hi + int(halo), int(n_total))
+
+
+class TorchComm:
+    """The two collectives of the path on torch tensors (NCCL on GPU, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def all_gather(self, t):
+        import torch
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group) \
+            if t.is_cuda else self.dist.all_gather(list(out.unbind(0)), t.contiguous(), group=self.group)
+        return out
+
+    def all_reduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+def sharded_seq_match(ops, comm, qrows, test_ids, seq_lens, k_probe):
+    """Backend-agnostic orchestration; see the module docstring.  Returns (pred_ids, pred_scores)."""
+    D_loc, I_loc = ops.local_topk(qrows, k_probe)
+    D_all = comm.all_gather(D_loc)
+    I_all = comm.all_gather(I_loc)
+    _, I = ops.merge(D_all, I_all)
+    cand_ids, cand_scores, n_cand = ops.cand_scores(qrows, test_ids, seq_lens, k_probe, I)
+    cand_scores = comm.all_reduce_max(cand_scores)
+    return ops.top(cand_ids, cand_scores, n_cand, len(seq_lens))
+
+
+class GpuOps:
+    """Local work of ``sharded_seq_match`` on this rank's GPU through the C ABI (torch CUDA tensors
+    carry the memory; libnafp runs on torch's current stream)."""
+
+    def __init__(self, index, n_query_rows, n_rows_global, owned_lo, owned_hi, max_len):
+        import torch
+        from ._lib import check, lib
+        self.torch, self.lib, self.check = torch, lib, check
+        self.index = index
+        self.n_query_rows = int(n_query_rows)
+        self.n_rows_global = int(n_rows_global)
+        self.owned = (int(owned_lo), int(owned_hi))
+        self.max_len = int(max_len)
+        self.dev = torch.device('cuda', index.ctx.device)
+        index.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def gather(self, q_dev, test_ids_dev):
+        n_test = test_ids_dev.numel()
+        qrows = self.torch.empty((n_test * self.max_len, 128), dtype=self.torch.float32, device=self.dev)
+        self.check(self.lib.nafp_seq_gather_dev(self.index.ctx.h, self._p(q_dev), self.n_query_rows, self._p(test_ids_dev),
+                                                n_test, self.max_len, self._p(qrows)))
+        return qrows
+
+    def local_topk(self, qrows, k):
+        n = qrows.shape[0]
+        D = self.torch.empty((n, k), dtype=self.torch.float32, device=self.dev)
+        I = self.torch.empty((n, k), dtype=self.torch.int64, device=self.dev)
+        self.check(self.lib.nafp_index_search_dev(self.index.h, self._p(qrows), n, k, self._p(D), self._p(I)))
+        return D, I
+
+    def merge(self, D_all, I_all):
+        W, n, k = D_all.shape
+        D = self.torch.empty((n, k), dtype=self.torch.float32, device=self.dev)
+        I = self.torch.empty((n, k), dtype=self.torch.int64, device=self.dev)
+        self.check(self.lib.nafp_topk_merge_dev(self.index.ctx.h, self._p(D_all), self._p(I_all), W, n, k, self._p(D), self._p(I)))
+        return D, I
+
+    def cand_scores(self, qrows, test_ids_dev, seq_lens_dev, k, I):
+        n_test, n_len = test_ids_dev.numel(), seq_lens_dev.numel()
+        cid = self.torch.empty((n_test, SEQ_MAXC), dtype=self.torch.int64, device=self.dev)
+        csc = self.torch.empty((n_test, n_len, SEQ_MAXC), dtype=self.torch.float32, device=self.dev)
+        nc = self.torch.empty((n_test,), dtype=self.torch.int32, device=self.dev)
+        self.check(self.lib.nafp_seq_cand_dev(self.index.h, self._p(qrows), self.n_query_rows, self._p(test_ids_dev), n_test,
+                                              self._p(seq_lens_dev), n_len, self.max_len, k, self._p(I), self.n_rows_global,
+                                              self.owned[0], self.owned[1], self._p(cid), self._p(csc), self._p(nc)))
+        return cid, csc, nc
+
+    def top(self, cand_ids, cand_scores, n_cand, n_len):
+        n_test = cand_ids.shape[0]
+        pid = self.torch.empty((n_test, n_len, N_PRED), dtype=self.torch.int64, device=self.dev)
+        psc = self.torch.empty((n_test, n_len, N_PRED), dtype=self.torch.float32, device=self.dev)
+        self.check(self.lib.nafp_seq_top_dev(self.index.ctx.h, n_test, n_len, self._p(cand_ids), self._p(cand_scores),
+                                             self._p(n_cand), self._p(pid), self._p(psc)))
+        return pid, psc
+
+
+class ShardedFlatIndex:
+    """Rank-local block (+ halo) of a row-sharded flat index and the collective sequence matcher."""
+
+    def __init__(self, n_rows_global, rank, world, max_len=19, device=None, comm=None):
+        from .eval.utils.get_index import FLAT_L2, Index
+        self.rank, self.world = int(rank), int(world)
+        self.n_rows_global = int(n_rows_global)
+        self.max_len = int(max_len)
+        self.lo, self.hi, self.hi_halo = shard_with_halo(n_rows_global, rank, world, max_len - 1)
+        self.index = Index(FLAT_L2, 128, device=self.rank if device is None else device)
+        self.index.reserve(self.hi_halo - self.lo)
+        self.index.set_label_offset(self.lo)
+        self.comm = comm
+        self._ops = None
+
+    @property
+    def ntotal(self):
+        return self.n_rows_global
+
+    def local_rows_needed(self):
+        """Global row range [lo, hi_halo) this rank must add, in order."""
+        return self.lo, self.hi_halo
+
+    def add_local(self, x):
+        self.index.add(x)
+        self._finish_if_complete()
+
+    def add_local_dev(self, dev_ptr, n):
+        self.index.add_dev(dev_ptr, n)
+        self._finish_if_complete()
+
+    def _finish_if_complete(self):
+        if self.index.ntotal == self.hi_halo - self.lo:
+            self.index.set_search_rows(self.hi - self.lo)
+
+    def add_from(self, parts):
+        """``parts``: row-indexable arrays (e.g. the dummy_db and db memmaps) forming the global database."""
+        base = 0
+        for p in parts:
+            n = len(p)
+            a, b = max(self.lo, base), min(self.hi_halo, base + n)
+            if a < b:
+                self.index.add(p[a - base:b - base])
+            base += n
+        assert base == self.n_rows_global, (base, self.n_rows_global)
+        self._finish_if_complete()
+
+    def ops(self, n_query_rows):
+        if self._ops is None or self._ops.n_query_rows != n_query_rows:
+            self._ops = GpuOps(self.index, n_query_rows, self.n_rows_global, self.lo, self.hi, self.max_len)
+        return self._ops
+
+    def seq_match_dev(self, q_dev, test_ids_dev, seq_lens_dev, k_probe=20):
+        """Everything on device tensors (torch); returns device tensors."""
+        ops = self.ops(q_dev.shape[0])
+        qrows = ops.gather(q_dev, test_ids_dev)
+        if self.world == 1 and self.comm is None:
+            D, I = ops.local_topk(qrows, k_probe)
+            cid, csc, nc = ops.cand_scores(qrows, test_ids_dev, seq_lens_dev, k_probe, I)
+            return ops.top(cid, csc, nc, seq_lens_dev.numel())
+        return sharded_seq_match(ops, self.comm, qrows, test_ids_dev, seq_lens_dev, k_probe)
+
+    def seq_match(self, query, test_ids, seq_lens, k_probe=20):
+        """Host arrays in, host arrays out (includes H2D / D2H)."""
+        import torch
+        dev = torch.device('cuda', self.index.ctx.device)
+        q = torch.from_numpy(np.ascontiguousarray(query, dtype=np.float32)).to(dev, non_blocking=True)
+        ids = torch.from_numpy(np.ascontiguousarray(test_ids, dtype=np.int64)).to(dev, non_blocking=True)
+        sl = torch.from_numpy(np.ascontiguousarray(seq_lens, dtype=np.int32)).to(dev, non_blocking=True)
+        pid, psc = self.seq_match_dev(q, ids, sl, k_probe)
+        return pid.cpu().numpy(), psc.cpu().numpy()

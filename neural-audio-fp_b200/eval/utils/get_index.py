@@ -113,6 +113,13 @@ class Index:
         return dict(rows=int(out[0]), fallback_rows=int(out[1]), passes=int(out[2]), reranked=int(out[3]),
                     fallback_overflow=int(out[5]), fallback_bound=int(out[6]))
 
+    def profile_scans(self, enable=True):
+        """(total ms, launches) of the scan kernel since the previous call; arms / disarms the timer."""
+        ms = ctypes.c_double()
+        n = ctypes.c_int64()
+        check(lib.nafp_index_profile_scans(self.h, int(bool(enable)), ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
     def seq_match(self, query, test_ids, seq_lens, k_probe=20):
         """Batched body of the reference's evaluation loop (``eval/eval_faiss.py:204-232``).
         Returns pred_ids (n_test, n_len, 10) int64 (-1 padded) and their scores."""
