@@ -40,8 +40,8 @@ SEQ_LENS = [1, 3, 5, 9, 11, 19]
 K_PROBE = 20
 FP_SEGS_PER_STEP = 1000          # 8 groups of TS_BATCH_SZ = 125
 FLOPS_PER_SEGMENT = 607_199_232  # model/arch.py (conv + div-enc)
-SAMPLE_ROWS = 500_000            # CPU baseline: database sample
-SAMPLE_IDS = 50                  # CPU baseline: test ids per step
+SAMPLE_ROWS = 250_000            # CPU baseline: database sample
+SAMPLE_IDS = 30                  # CPU baseline: test ids per step
 
 
 def _peaks():
@@ -256,6 +256,8 @@ def run_gpu(args):
         return float(t.item())
 
     ctx = Context.get(local_rank)
+    # all torch work (copies, NCCL, CUDA events) on the stream the library launches its kernels on
+    torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.stream, device=dev))
     hbm_peak, tf_burst, tf_sustained, peak_src = _peaks()
     n_dummy = args.db_rows
     n_total = n_dummy + N_DB

@@ -96,8 +96,9 @@ __global__ void flat_prep_kernel(const float* __restrict__ q, int nq, int nq_pad
 // the scan
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_STAGES = 4;
-constexpr int SCAN_THREADS = 352;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue, warp 10 reducer
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
+constexpr int SCAN_THREADS = (3 + EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..17 epilogue, warp 18 reducer
+constexpr int EPI_PARTS = EPI_WARPS / 4;          // column interleave: warp takes every EPI_PARTS-th 32-query chunk
 constexpr int STAGE_BYTES = TILE_ROWS * D128 * 2;          // 32 KB: two 64-column K blocks of 16 KB
 constexpr int KBLOCK_BYTES = TILE_ROWS * 128;              // 16 KB
 constexpr int Q_BYTES_MAX = NQ_MAX * D128 * 2;             // 64 KB
@@ -124,6 +125,16 @@ __device__ __forceinline__ int smem_atom_inc(int* p) {
     int old;
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
     return old;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ int smem_ld_volatile(const int* p) {
     int v;
@@ -209,7 +220,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int i = 0; i < n_iter; ++i) {
                 const int s = i % SCAN_STAGES;
                 const uint32_t ph = (i / SCAN_STAGES) & 1;
-                mbar_wait(&bars->empty[s], ph ^ 1);
+                mbar_wait_parked(&bars->empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
                 const int tile = t0 + (i < n_own ? i : i - n_own);
                 uint8_t* dst = a_s + s * STAGE_BYTES;
@@ -232,8 +243,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const uint32_t ph = (i / SCAN_STAGES) & 1;
                 const int acc = i & 1;
                 const uint32_t aph = (i >> 1) & 1;
-                mbar_wait(&bars->tempty[acc], aph ^ 1);
-                mbar_wait(&bars->full[s], ph);
+                mbar_wait_parked(&bars->tempty[acc], aph ^ 1);
+                mbar_wait_parked(&bars->full[s], ph);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * NQ_MAX;
 #pragma unroll
@@ -252,18 +263,21 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         __syncwarp();
     } else if (warp < 2 + EPI_WARPS) {
-        // ------------------------------------------------------------ epilogue (8 warps)
+        // ------------------------------------------------------------ epilogue (EPI_WARPS warps)
         // Warp e reads TMEM lane quadrant (warp & 3) -- its 32 DB rows of the tile -- and takes every
         // other 32-query chunk (half = e >> 2), so two warps per SM sub-partition hide each other's
         // tcgen05.ld latency.  Each warp keeps a private copy of the thresholds of its own chunks.
         const int qd = warp & 3;
-        const int e = warp - 2;           // 0..7
-        const int half = e >> 2;
+        const int e = warp - 2;           // 0..EPI_WARPS-1
+        const int half = e >> 2;          // column part 0..EPI_PARTS-1
+        constexpr int CSTEP = 32 * EPI_PARTS;        // distance between this warp's chunks
+        constexpr int NTHR = NQ_MAX / CSTEP;         // chunks (hence threshold registers) per warp
+        constexpr int QPW = NQ_MAX / EPI_WARPS;      // queries whose maxima this warp publishes
         float* my_thr = thr_s + e * NQ_MAX;
         int pub = INT_MIN;
-        int thr_ord[NQ_MAX / 64];
+        int thr_ord[NTHR];
 #pragma unroll
-        for (int r = 0; r < NQ_MAX / 64; ++r) thr_ord[r] = NEG_INF_ORD;
+        for (int r = 0; r < NTHR; ++r) thr_ord[r] = NEG_INF_ORD;
         uint64_t* my_pool = pool + static_cast<int64_t>(cta) * NQ_MAX * POOL_CAP;
         bool normal = false;      // warp-uniform: thresholds of all of this warp's queries are known
         bool all_valid = false;
@@ -286,10 +300,10 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             h_next = load_h(i + 1);
             // shared thresholds of this warp's chunks: loads issued now, consumed after the tile
             const bool refresh = i < 12 || (i & 3) == 0 || i == n_own - 1;
-            int tg[NQ_MAX / 64];
+            int tg[NTHR];
 #pragma unroll
-            for (int r = 0; r < NQ_MAX / 64; ++r) {
-                const int q = half * 32 + r * 64 + lane;
+            for (int r = 0; r < NTHR; ++r) {
+                const int q = half * 32 + r * CSTEP + lane;
                 tg[r] = (refresh && q < nq_pad) ? ld_relaxed(&Tg[q]) : INT_MIN;
             }
             if (!normal && ((i >= 1 && all_valid) || i >= MAXONLY_CAP)) {
@@ -307,10 +321,9 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * NQ_MAX;
             if (!skip) {
-                for (int c0 = half * 32; c0 < nq_pad; c0 += 64) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c0, v);
-                    tc_wait_ld();
+                // one 32-column chunk: max-only tiles feed the running maxima, normal tiles keep the
+                // scores above the shared threshold (4 independent predicate chains, no serial OR)
+                auto process = [&](const uint32_t (&v)[32], int c0) {
                     if (maxonly) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -319,40 +332,53 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             if (lane == j) smem_red_max(&lmax_s[c0 + j], m);
                         }
                     } else {
-                        bool anyp = false;
-                        const float4* thr4 = reinterpret_cast<const float4*>(my_thr + c0);
+                        bool p0 = false, p1 = false, p2 = false, p3 = false;
+                        const uint32_t thr_addr = smem_u32(my_thr + c0);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 t4 = thr4[j4];
-                            anyp |= (__uint_as_float(v[4 * j4 + 0]) - h) > t4.x;
-                            anyp |= (__uint_as_float(v[4 * j4 + 1]) - h) > t4.y;
-                            anyp |= (__uint_as_float(v[4 * j4 + 2]) - h) > t4.z;
-                            anyp |= (__uint_as_float(v[4 * j4 + 3]) - h) > t4.w;
+                            const float4 t4 = lds_f4(thr_addr + 16 * j4);
+                            p0 |= (__uint_as_float(v[4 * j4 + 0]) - h) > t4.x;
+                            p1 |= (__uint_as_float(v[4 * j4 + 1]) - h) > t4.y;
+                            p2 |= (__uint_as_float(v[4 * j4 + 2]) - h) > t4.z;
+                            p3 |= (__uint_as_float(v[4 * j4 + 3]) - h) > t4.w;
                         }
-                        if (__any_sync(0xffffffffu, anyp)) {
+                        // rare: some lane beat a threshold.  Only the column classes (j mod 4) that fired are re-scanned.
+                        const bool pr[4] = {p0, p1, p2, p3};
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float s = __uint_as_float(v[j]) - h;
-                                if (s > my_thr[c0 + j]) {
-                                    const int so = f2ord(s);
-                                    const int pos = smem_atom_inc(&cnt_s[c0 + j]);
-                                    if (pos < POOL_CAP)
-                                        my_pool[(c0 + j) * POOL_CAP + pos] =
-                                            (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
-                                    smem_red_max(&lmax_s[c0 + j], so);
+                        for (int r = 0; r < 4; ++r) {
+                            if (__any_sync(0xffffffffu, pr[r])) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; ++j4) {
+                                    const int j = 4 * j4 + r;
+                                    const float s = __uint_as_float(v[j]) - h;
+                                    if (s > lds_f1(thr_addr + 4 * j)) {
+                                        const int so = f2ord(s);
+                                        const int pos = smem_atom_inc(&cnt_s[c0 + j]);
+                                        if (pos < POOL_CAP)
+                                            my_pool[(c0 + j) * POOL_CAP + pos] =
+                                                (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
+                                        smem_red_max(&lmax_s[c0 + j], so);
+                                    }
                                 }
                             }
                         }
                     }
+                };
+                // 4 warps per SM sub-partition hide each other's tcgen05.ld / dependency latencies
+                for (int c0 = half * 32; c0 < nq_pad; c0 += CSTEP) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    tc_wait_ld();
+                    process(v, c0);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tempty[acc]);
-            // publish this CTA's running maxima: warp e owns queries [32 e, 32 e + 32)
+            // publish this CTA's running maxima: warp e owns queries [QPW e, QPW e + QPW)
             {
-                const int q = e * 32 + lane;
-                if (q < nq_pad) {
+                const int q = e * QPW + lane;
+                if (lane < QPW && q < nq_pad) {
                     const int m = smem_ld_volatile(&lmax_s[q]);
                     if (m > pub) {
                         st_relaxed(&Mx[q * G + cta], m);
@@ -364,13 +390,13 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (refresh) {
                 bool valid = true;
 #pragma unroll
-                for (int r = 0; r < NQ_MAX / 64; ++r) {
-                    const int q = half * 32 + r * 64 + lane;
+                for (int r = 0; r < NTHR; ++r) {
+                    const int q = half * 32 + r * CSTEP + lane;
                     if (q < nq_pad) {
                         if (tg[r] > thr_ord[r]) {
                             if (dbg_first && qd == 0 && thr_ord[r] == NEG_INF_ORD) dbg_first[cta * NQ_MAX + q] = i;
                             thr_ord[r] = tg[r];
-                            my_thr[q] = ord2f(tg[r]);
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(my_thr + q)), "f"(ord2f(tg[r])) : "memory");
                         }
                         valid = valid && (thr_ord[r] > NEG_INF_ORD);
                     }
@@ -393,10 +419,10 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         __syncwarp();
         // all epilogue warps are done appending before counts are published
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         {
-            const int q = e * 32 + lane;
-            if (q < nq_pad) {
+            const int q = e * QPW + lane;
+            if (lane < QPW && q < nq_pad) {
                 const int c = cnt_s[q];
                 cnt[cta * NQ_MAX + q] = min(c, POOL_CAP);
                 if (c > POOL_CAP) flags[q] = 1;      // pool overflow -> exact fallback answers this query
@@ -404,7 +430,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         if (lane == 0) smem_atom_inc(&bars->done);
     } else {
-        // ------------------------------------------------------------ threshold reducer (warp 10)
+        // ------------------------------------------------------------ threshold reducer (last warp)
         // For the queries assigned to this CTA: T = kg-th largest of the per-CTA maxima.  At least kg
         // distinct rows score >= T, so dropping rows that score <= T can never lose a top-kg row.
         while (smem_ld_volatile(&bars->done) < EPI_WARPS) {

@@ -81,7 +81,11 @@ class GpuOps:
         self.owned = (int(owned_lo), int(owned_hi))
         self.max_len = int(max_len)
         self.dev = torch.device('cuda', index.ctx.device)
-        index.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        # torch work (allocations, copies, NCCL, events) must be ordered with libnafp's kernels: make
+        # the library's stream torch's current stream (torch's default stream handle is 0, which the
+        # C ABI cannot adopt, so the adoption goes this way round)
+        self.stream = torch.cuda.ExternalStream(index.ctx.stream, device=self.dev)
+        torch.cuda.set_stream(self.stream)
 
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
