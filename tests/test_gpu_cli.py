@@ -1,0 +1,76 @@
+"""GPU end-to-end: the generate and evaluate entry points on a small synthetic corpus, against the
+oracle pipeline run on the same WAV files (BASELINE configs[0] in miniature)."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def corpus(tmp_path_factory):
+    from nafp_b200 import synth
+    root = tmp_path_factory.mktemp("corpus")
+    src = root / "music"
+    for sub in ("test-dummy-db-100k-full/a", "test-query-db-500-30s/query/a", "test-query-db-500-30s/db/a"):
+        os.makedirs(src / sub)
+    for i in range(12):                                    # dummy: 12 x 12 s
+        synth.write_wav(str(src / "test-dummy-db-100k-full/a" / f"d{i:03d}.wav"), synth.synth_track(100 + i, 96000))
+    for i in range(4):                                     # db / query: 4 x 10 s, query = db + noise at 5 dB SNR
+        x = synth.synth_track(200 + i, 80000)
+        synth.write_wav(str(src / "test-query-db-500-30s/db/a" / f"s{i:03d}.wav"), x)
+        synth.write_wav(str(src / "test-query-db-500-30s/query/a" / f"s{i:03d}.wav"), synth.add_noise_snr(x, 5.0, i))
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "default.yaml")))
+    cfg['DIR']['SOURCE_ROOT_DIR'] = str(src) + "/"
+    cfg['DIR']['LOG_ROOT_DIR'] = str(root / "logs") + "/"
+    cfg['DIR']['OUTPUT_ROOT_DIR'] = str(root / "logs" / "emb") + "/"
+    cfg['DATA_SEL']['TEST_DUMMY_DB'] = '100k_full_icassp'
+    cfg['BSZ']['TS_BATCH_SZ'] = 25
+    return cfg, src
+
+
+def test_generate_then_evaluate(corpus):
+    import glob
+    from nafp_b200.eval.eval_search import run_eval
+    from nafp_b200.model import weights as W
+    from nafp_b200.model.generate import generate_fingerprint
+    from oracle import fingerprinter as ofp
+    from oracle import melspec, segments, seq_match
+    from oracle.flat_index import FlatL2
+    cfg, src = corpus
+    generate_fingerprint(cfg, 'random-init:7', None, None, None, False)
+    emb_dir = cfg['DIR']['OUTPUT_ROOT_DIR'] + '/random-init:7/0/'
+    w = W.init_weights(7)
+    got = {}
+    for key, sub in (("dummy_db", "test-dummy-db-100k-full/"), ("query", "test-query-db-500-30s/query/"),
+                     ("db", "test-query-db-500-30s/db/")):
+        shape = np.load(emb_dir + f"{key}_shape.npy")
+        arr = np.memmap(emb_dir + f"{key}.mm", dtype='float32', mode='r', shape=tuple(shape))
+        files = sorted(glob.glob(str(src / sub) + '**/*.wav', recursive=True))
+        ref = np.concatenate([ofp.fingerprinter(melspec.melspec_layer(b), w) for b in segments.batches(files, bsz=25)])
+        assert arr.shape == ref.shape == (shape[0], 128)
+        assert (np.asarray(arr) * ref).sum(1).min() >= 0.9999 and np.abs(np.asarray(arr) - ref).max() <= 1e-3
+        got[key] = np.array(arr)
+    assert got["dummy_db"].shape[0] == 12 * 23 and got["db"].shape[0] == 4 * 19
+
+    ids_path = emb_dir + "ids.npy"
+    test_ids = np.arange(0, got["query"].shape[0] - 9, 3)
+    np.save(ids_path, test_ids)
+    rates = run_eval(emb_dir, index_type='l2', test_ids=ids_path, test_seq_len='1 3 5 9', k_probe=20, display_interval=5,
+                     live=False)
+    raw = np.load(emb_dir + "raw_score.npy")
+    assert (np.load(emb_dir + "test_ids.npy") == test_ids).all()
+    # the oracle evaluation on the SAME (GPU-generated) fingerprints must agree flag by flag
+    idx = FlatL2(128)
+    idx.add(got["dummy_db"])
+    idx.add(got["db"])
+    raw_o, _ = seq_match.evaluate(idx, got["query"], np.concatenate([got["dummy_db"], got["db"]]), len(got["dummy_db"]),
+                                  test_ids, [1, 3, 5, 9], 20)
+    assert raw.shape == raw_o.shape == (len(test_ids), 16)
+    assert (raw != raw_o).sum() <= 1                      # at most one fp32-tie flip
+    assert np.abs(np.array(rates) - seq_match.hit_rates(raw_o, 4)).max() <= 100.0 / len(test_ids) + 1e-9
+    assert not os.path.exists(emb_dir + "dummy_db.mm.bak")
+    assert os.path.getsize(emb_dir + "dummy_db.mm") == 12 * 23 * 128 * 4      # inputs are never extended on disk
