@@ -47,6 +47,7 @@ struct ConvGeom {
 struct ConvParams {
     int m_total, ms, c_in, c_out, nt, n_ntiles, n_mtiles;
     int mode, pad_lo, tap_lo, tap_hi, kb_per_tap, tps, bf, bb;
+    int groups;      // 32-row groups per segment (>= 1): slots of the LayerNorm partial sums
 };
 
 struct EncoderState {
@@ -60,6 +61,7 @@ struct EncoderState {
     __half* y = nullptr;                       // pre-LayerNorm scratch, largest layer
     __half* x[ENC_LAYERS] = {};                // normalised activations
     float* stats = nullptr;                    // [ENC_LAYERS][ENC_CHUNK][2]
+    float* part = nullptr;                     // [ENC_CHUNK][128][2] partial LayerNorm sums of the running layer
     float* mel = nullptr;                      // (ENC_CHUNK, 256, 32) for the fused entry points
     void* xin = nullptr;                       // (ENC_CHUNK, 8000) staging for the *_host entry points
     float* emb = nullptr;                      // (ENC_CHUNK, 128)
@@ -119,7 +121,7 @@ __device__ __forceinline__ float elu(float v) { return v > 0.f ? v : __expf(v) -
 __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int64_t seg0,
              int n_seg, const float* __restrict__ w0, const float* __restrict__ b0, __half* __restrict__ y,
-             float* __restrict__ stats) {
+             float* __restrict__ part) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.y;
     if (seg >= n_seg) return;
@@ -170,10 +172,8 @@ conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, in
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0) {
-        atomicAdd(stats + 2 * seg, s1);
-        atomicAdd(stats + 2 * seg + 1, s2);
-    }
+    if (lane == 0)      // one slot per (segment, block, warp): summed in fixed order by ln_stats_kernel
+        reinterpret_cast<float2*>(part)[static_cast<int64_t>(seg) * 64 + blockIdx.x * 8 + warp] = make_float2(s1, s2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -196,7 +196,7 @@ struct ConvBars {
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvParams p, const float* __restrict__ bias, __half* __restrict__ y,
-                 float* __restrict__ stats) {
+                 float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.nt * 128;
@@ -335,7 +335,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tempty[acc]);
-            // LayerNorm statistics: reduce over the rows of the same segment, one atomic per group
+            // LayerNorm statistics: reduce over the rows of the same segment inside the warp, then one
+            // slot per (segment, 32-row group, N tile, column half) -- no atomics, so the sums (and with
+            // them every fingerprint) are bit-reproducible
             if (!row_ok) { s1 = 0.f; s2 = 0.f; }
             for (int o = 1; o < seg_len; o <<= 1) {
                 s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -343,8 +345,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (row_ok && (lane & (seg_len - 1)) == 0) {
                 const int b = m / p.ms;
-                atomicAdd(stats + 2 * b, s1);
-                atomicAdd(stats + 2 * b + 1, s2);
+                const int grp = p.ms >= 32 ? (m % p.ms) >> 5 : 0;
+                const int64_t slot = ((static_cast<int64_t>(b) * p.groups + grp) * p.n_ntiles + ntile) * 2 + half;
+                reinterpret_cast<float2*>(part)[slot] = make_float2(s1, s2);
             }
         }
     }
@@ -352,6 +355,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// per-segment (sum, sum of squares) from the partial slots, fixed summation order; one warp per segment
+__global__ void __launch_bounds__(256)
+ln_stats_kernel(const float* __restrict__ part, int slots, int n_seg, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (seg >= n_seg) return;
+    const float2* p = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(seg) * slots;
+    double a = 0.0, b = 0.0;
+    for (int i = lane; i < slots; i += 32) {
+        const float2 v = p[i];
+        a += v.x;
+        b += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        stats[2 * seg] = static_cast<float>(a);
+        stats[2 * seg + 1] = static_cast<float>(b);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -459,6 +486,7 @@ static int encoder_init(nafp_ctx* ctx) {
     }
     NAFP_CUDA(cudaMalloc(&s->y, (static_cast<size_t>(ENC_CHUNK) * ymax + 128 * 1024) * sizeof(__half)));
     NAFP_CUDA(cudaMalloc(&s->stats, static_cast<size_t>(ENC_LAYERS) * ENC_CHUNK * 2 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->part, static_cast<size_t>(ENC_CHUNK) * 128 * 2 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->dw1, 128 * 8 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->db1, 128 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->dw2, 128 * 32 * sizeof(float)));
@@ -509,7 +537,7 @@ void encoder_destroy(nafp_ctx* ctx) {
         cudaFree(s->x[l]); cudaFree(s->bias[l]); cudaFree(s->ln_g[l]); cudaFree(s->ln_b[l]);
         if (s->wt[l]) cudaFree(s->wt[l]);
     }
-    void* bufs[] = {s->w0, s->y, s->stats, s->dw1, s->db1, s->dw2, s->db2, s->mel, s->xin, s->emb};
+    void* bufs[] = {s->w0, s->y, s->stats, s->part, s->dw1, s->db1, s->dw2, s->db2, s->mel, s->xin, s->emb};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     ctx->encoder = nullptr;
@@ -520,24 +548,28 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
                         float* emb_dev) {
     EncoderState* s = ctx->encoder;
     cudaStream_t st = ctx->stream;
-    NAFP_CUDA(cudaMemsetAsync(s->stats, 0, static_cast<size_t>(ENC_LAYERS) * ENC_CHUNK * 2 * sizeof(float), st));
     for (int l = 0; l < ENC_LAYERS; ++l) {
         const ConvGeom& L = s->g[l];
         float* stats = s->stats + static_cast<size_t>(l) * ENC_CHUNK * 2;
         const int per = L.ms * L.c_out;
+        int slots;
         if (l == 0) {
-            conv0_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, seg0, n, s->w0, s->bias[0], s->y, stats);
+            conv0_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, seg0, n, s->w0, s->bias[0], s->y, s->part);
+            slots = 64;
         } else {
             ConvParams p;
             p.m_total = n * L.ms; p.ms = L.ms; p.c_in = L.c_in; p.c_out = L.c_out; p.nt = L.nt;
             p.n_ntiles = L.c_out / L.nt; p.n_mtiles = (p.m_total + 127) / 128;
             p.mode = L.mode; p.pad_lo = L.pad_lo; p.tap_lo = L.tap_lo; p.tap_hi = L.tap_hi;
             p.kb_per_tap = L.c_in / 64; p.tps = L.ms >= 128 ? L.ms / 128 : 0; p.bf = L.bf; p.bb = L.bb;
+            p.groups = L.ms >= 32 ? L.ms / 32 : 1;
+            slots = p.groups * p.n_ntiles * 2;
             const int tiles = p.n_mtiles * p.n_ntiles;
             const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-            conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, stats);
+            conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, s->part);
         }
-        ctx->launches++;
+        ln_stats_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->part, slots, n, stats);
+        ctx->launches += 2;
         if (l < ENC_LAYERS - 1 || true) {
             const int64_t total8 = static_cast<int64_t>(n) * per / 8;
             ln_apply_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, st>>>(s->y, stats, s->ln_g[l], s->ln_b[l],

@@ -37,9 +37,10 @@ class Melspec:
         self.ctx = ctx or Context.get(device)
 
     def __call__(self, x, group_size=None):
-        x = np.ascontiguousarray(x, dtype=np.float32).reshape(len(x), -1)
-        if x.shape[1] != 8000:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.size != len(x) * 8000:
             raise ValueError("expected (B, 1, 8000) segments")
+        x = x.reshape(len(x), 8000)
         n = x.shape[0]
         g = int(group_size) if group_size else max(n, 1)
         out = np.empty((n, 256, 32, 1), dtype=np.float32)

@@ -49,7 +49,7 @@ def test_generate_then_evaluate(corpus):
                      ("db", "test-query-db-500-30s/db/")):
         shape = np.load(emb_dir + f"{key}_shape.npy")
         arr = np.memmap(emb_dir + f"{key}.mm", dtype='float32', mode='r', shape=tuple(shape))
-        files = sorted(glob.glob(str(src / sub) + '**/*.wav', recursive=True))
+        files = sorted(glob.glob(os.path.join(str(src), sub) + '**/*.wav', recursive=True))
         ref = np.concatenate([ofp.fingerprinter(melspec.melspec_layer(b), w) for b in segments.batches(files, bsz=25)])
         assert arr.shape == ref.shape == (shape[0], 128)
         assert (np.asarray(arr) * ref).sum(1).min() >= 0.9999 and np.abs(np.asarray(arr) - ref).max() <= 1e-3

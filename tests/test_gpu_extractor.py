@@ -82,8 +82,8 @@ def test_many_segments_chunking_property(models):
     big = np.tile(x, (17, 1))[:2100]               # 16 full groups + a partial one
     emb = m_fp.fingerprint(big, group_size=125)
     one = m_fp.fingerprint(x, group_size=125)
-    for g in range(16):
-        assert np.abs(emb[g * 125:(g + 1) * 125] - one).max() < 2e-4      # atomics order -> last-bit differences only
+    for g in range(16):       # LayerNorm sums use fixed-order partial slots (no atomics): bit-reproducible
+        np.testing.assert_array_equal(emb[g * 125:(g + 1) * 125], one)
     assert np.isfinite(emb).all() and np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
 
 
