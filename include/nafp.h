@@ -131,6 +131,10 @@ int nafp_index_train(nafp_index* idx, const float* x_host, int64_t n, int64_t se
 /* index.add(x) (eval/eval_faiss.py:147-148): appends n rows; labels are insertion order. */
 int nafp_index_add(nafp_index* idx, const float* x_host, int64_t n);
 int nafp_index_add_dev(nafp_index* idx, const float* x_dev, int64_t n);
+/* IVF-PQ only: export / import the trained quantizers (coarse (nlist,128), pq (M,256,128/M), float32),
+ * e.g. to reuse one training across shards; import is only allowed on an empty index. */
+int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_host);
+int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const float* pq_host);
 /* pre-size the device store (optional; avoids regrowth copies for very large databases) */
 int nafp_index_reserve(nafp_index* idx, int64_t n_total);
 int64_t nafp_index_ntotal(nafp_index* idx);

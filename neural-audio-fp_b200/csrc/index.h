@@ -13,7 +13,8 @@ constexpr int NQ_MAX = 256;          // query rows per scan pass (MMA N)
 constexpr int TILE_ROWS = 128;       // DB rows per MMA tile (MMA M)
 constexpr int POOL_CAP = 128;        // candidate slots per (CTA, query) per pass
 constexpr int MAX_K = 128;
-constexpr int BRUTE_CHUNKS = 64;
+constexpr int BRUTE_CHUNKS = 296;        // CTAs per query of the exact fallback scan (2 per SM)
+constexpr int BRUTE_SLOTS = 32;          // queries per fallback launch
 constexpr int SELECT_CAP = 2048;     // candidates re-ranked in fp32 per query, at most
 
 struct IvfPq;                        // ivfpq.cu
@@ -47,9 +48,10 @@ struct nafp_index {
     uint64_t* pool = nullptr;         // [grid][NQ_MAX][POOL_CAP]
     int32_t* cnt = nullptr;           // [grid][NQ_MAX]
     int32_t* flags = nullptr;         // [NQ_MAX] != 0 -> answered by the exact fallback
-    int32_t* fb_list = nullptr;       // [NQ_MAX] query rows handed to the fallback, + count
-    int32_t* fb_count = nullptr;
-    uint64_t* brute_part = nullptr;   // [NQ_MAX][BRUTE_CHUNKS][MAX_K]
+    int64_t* gidx = nullptr;          // [NQ_MAX] global query row of every pass row
+    int32_t* fail_list = nullptr;     // [2 nq + 2] rows to retry / to scan exactly, + the two counters
+    int64_t fail_cap = 0;
+    uint64_t* brute_part = nullptr;   // [BRUTE_SLOTS][BRUTE_CHUNKS][MAX_K]
     unsigned long long* stats = nullptr;   // [8] device counters
     int32_t* dbg_first = nullptr;     // developer probe: [grid][NQ_MAX] tile index of the first shared threshold
     // staging for the host entry points

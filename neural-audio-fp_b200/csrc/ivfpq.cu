@@ -1,18 +1,640 @@
-// IVF-PQ index -- placeholder translation unit until the kernels land.
+// IVF-PQ index: faiss.IndexIVFPQ(IndexFlatL2(d), d, nlist=256, M=64, nbits=8) as the
+// reference builds it (eval/utils/get_index_faiss.py:69-74), trained by k-means (:105-117), searched
+// with nprobe = 40 (:120).  L2 metric, residual encoding, dsub = d / M.
+//
+//   train   k-means (Lloyd, 25 iterations, <= 256 points per centroid, seeded) for the coarse
+//           quantizer, then one k-means per sub-space on the residuals; deterministic (fixed-order sums)
+//   add     ivfpq_encode_kernel: nearest coarse centroid + 64 one-byte codes per row; the inverted
+//           lists are a stable counting sort of (list, row) rebuilt lazily before the next search
+//   search  ivfpq_probe_kernel (nprobe nearest lists per query row) ->
+//           ivfpq_scan_kernel  (one CTA per (query row, probed list): 64 x 256 fp32 look-up table in
+//                               shared memory, ADC scan of the list's codes, block top-k) ->
+//           topk merge of the nprobe partial lists.
+// HBM-bound: 0.156 * N * 68 bytes per query row at nprobe / nlist = 40 / 256.
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <vector>
+
 #include "index.h"
+#include "ptx.cuh"
 
 namespace nafp {
-int ivfpq_create(nafp_index*, int, int, int) {
-    set_error("IVF-PQ kernels are not built yet");
-    return NAFP_ERR_UNSUPPORTED;
+
+constexpr int PQ_MAX_M = 64;
+constexpr int PQ_KSUB = 256;
+constexpr int IVF_MAX_NLIST = 1024;
+constexpr int IVF_SCAN_CAP = 1024;        // candidate buffer per (query, list) CTA
+
+struct IvfPq {
+    int nlist = 256, m = 64, dsub = 2;
+    bool trained = false;
+    float* coarse = nullptr;      // [nlist][128]
+    float* pq = nullptr;          // [m][256][dsub]
+    int32_t* assign = nullptr;    // [cap] list of every row (row order)
+    uint8_t* codes = nullptr;     // [cap][m]
+    int64_t cap = 0;
+    // list-sorted copy
+    bool dirty = true;
+    uint8_t* lcodes = nullptr;    // [n][m]
+    int32_t* lids = nullptr;      // [n]
+    int32_t* loff = nullptr;      // [nlist + 1]
+    int64_t sorted_cap = 0;
+    // search scratch
+    int32_t* probes = nullptr;    // [nq_cap][nprobe_cap]
+    float* partD = nullptr;       // [nprobe][nq_cap][k]
+    int64_t* partI = nullptr;
+    int64_t scratch_nq = 0;
+    int scratch_nprobe = 0, scratch_k = 0;
+};
+
+// ------------------------------------------------------------------------------------------ k-means
+// nearest centroid of `dim`-dimensional points (row stride `ld` floats); one warp per point, lane l
+// scans centroids l, l+32, ...; ties go to the lower centroid id
+__global__ void kmeans_assign_kernel(const float* __restrict__ x, int64_t n, int ld, int dim,
+                                     const float* __restrict__ cent, int k, int32_t* __restrict__ assign,
+                                     float* __restrict__ dist_out) {
+    extern __shared__ float xs[];      // [warps][dim]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    float* xr = xs + w * dim;
+    for (int j = lane; j < dim; j += 32) xr[j] = x[i * ld + j];
+    __syncwarp();
+    float best = FLT_MAX;
+    int bi = INT_MAX;
+    for (int c = lane; c < k; c += 32) {
+        const float* cr = cent + static_cast<int64_t>(c) * dim;
+        float d = 0.f;
+        for (int j = 0; j < dim; ++j) {
+            const float t = xr[j] - __ldg(cr + j);
+            d += t * t;
+        }
+        if (d < best) { best = d; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+        assign[i] = bi;
+        if (dist_out) dist_out[i] = best;
+    }
 }
-void ivfpq_destroy(nafp_index*) {}
-int ivfpq_train(nafp_index*, const float*, int64_t, int64_t) { return NAFP_ERR_UNSUPPORTED; }
-int ivfpq_add_rows(nafp_index*, int64_t, int64_t) { return NAFP_ERR_UNSUPPORTED; }
-int ivfpq_search_dev(nafp_index*, const float*, int64_t, int, float*, int64_t*) { return NAFP_ERR_UNSUPPORTED; }
+
+// new centroid c = mean of its points; one block per centroid, fixed summation order; empty clusters keep
+// their previous centroid
+__global__ void kmeans_update_kernel(const float* __restrict__ x, int64_t n, int ld, int dim,
+                                     const int32_t* __restrict__ assign, float* __restrict__ cent) {
+    __shared__ double red[256];
+    __shared__ int cnt_s[256];
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x;
+    // every thread scans a strided share of the points; dims are looped (dim <= 128)
+    int cnt = 0;
+    for (int64_t i = tid; i < n; i += blockDim.x) cnt += assign[i] == c ? 1 : 0;
+    cnt_s[tid] = cnt;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) cnt_s[tid] += cnt_s[tid + s];
+        __syncthreads();
+    }
+    const int total = cnt_s[0];
+    __syncthreads();
+    if (total == 0) return;
+    for (int j = 0; j < dim; ++j) {
+        double acc = 0.0;
+        for (int64_t i = tid; i < n; i += blockDim.x)
+            if (assign[i] == c) acc += x[i * ld + j];
+        red[tid] = acc;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (tid < s) red[tid] += red[tid + s];
+            __syncthreads();
+        }
+        if (tid == 0) cent[static_cast<int64_t>(c) * dim + j] = static_cast<float>(red[0] / total);
+        __syncthreads();
+    }
+}
+
+__global__ void residual_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ coarse,
+                                const int32_t* __restrict__ assign, float* __restrict__ r) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= n * D128) return;
+    const int64_t i = idx / D128;
+    const int j = static_cast<int>(idx % D128);
+    r[idx] = x[idx] - coarse[static_cast<int64_t>(assign[i]) * D128 + j];
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, int ld, int dim, const int32_t* __restrict__ rows,
+                                   int k, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * dim) return;
+    out[idx] = x[static_cast<int64_t>(rows[idx / dim]) * ld + idx % dim];
+}
+
+static int run_kmeans(nafp_ctx* ctx, const float* x_dev, int64_t n, int ld, int dim, int k, float* cent_dev,
+                      int32_t* assign_dev, int niter, uint64_t seed) {
+    // initial centroids: k distinct training points chosen by a seeded shuffle
+    std::vector<int32_t> rows(n);
+    std::iota(rows.begin(), rows.end(), 0);
+    std::mt19937_64 rng(seed);
+    for (int64_t i = 0; i < std::min<int64_t>(k, n); ++i) {
+        std::uniform_int_distribution<int64_t> pick(i, n - 1);
+        std::swap(rows[i], rows[pick(rng)]);
+    }
+    std::sort(rows.begin(), rows.begin() + std::min<int64_t>(k, n));
+    int32_t* rows_dev = nullptr;
+    NAFP_CUDA(cudaMalloc(&rows_dev, k * sizeof(int32_t)));
+    std::vector<int32_t> first(k);
+    for (int i = 0; i < k; ++i) first[i] = rows[i % std::max<int64_t>(n, 1)];
+    NAFP_CUDA(cudaMemcpyAsync(rows_dev, first.data(), k * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    gather_rows_kernel<<<(k * dim + 255) / 256, 256, 0, ctx->stream>>>(x_dev, ld, dim, rows_dev, k, cent_dev);
+    const int threads = 256, warps = threads / 32;
+    const unsigned blocks = static_cast<unsigned>((n + warps - 1) / warps);
+    for (int it = 0; it < niter; ++it) {
+        kmeans_assign_kernel<<<blocks, threads, warps * dim * sizeof(float), ctx->stream>>>(x_dev, n, ld, dim, cent_dev, k,
+                                                                                         assign_dev, nullptr);
+        kmeans_update_kernel<<<k, 256, 0, ctx->stream>>>(x_dev, n, ld, dim, assign_dev, cent_dev);
+        ctx->launches += 2;
+    }
+    NAFP_CUDA(cudaGetLastError());
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(rows_dev);
+    return NAFP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ add
+// one warp per row: nearest coarse centroid, residual, then lane l encodes sub-spaces l and l + 32
+__global__ void __launch_bounds__(256)
+ivfpq_encode_kernel(const float* __restrict__ x32, int64_t row0, int64_t n, const float* __restrict__ coarse,
+                    int nlist, const float* __restrict__ pq, int m, int dsub, int32_t* __restrict__ assign,
+                    uint8_t* __restrict__ codes) {
+    __shared__ float xs[8][D128];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5); r < n; r += nwarps) {
+        const int64_t row = row0 + r;
+        float* xr = xs[w];
+        reinterpret_cast<float4*>(xr)[lane] = reinterpret_cast<const float4*>(x32 + row * D128)[lane];
+        __syncwarp();
+        float best = FLT_MAX;
+        int bi = INT_MAX;
+        for (int c = lane; c < nlist; c += 32) {
+            const float* cr = coarse + static_cast<int64_t>(c) * D128;
+            float d = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < D128; ++j) {
+                const float t = xr[j] - __ldg(cr + j);
+                d += t * t;
+            }
+            if (d < best) { best = d; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) assign[row] = bi;
+        // residual in place
+        {
+            const float4 cv = reinterpret_cast<const float4*>(coarse + static_cast<int64_t>(bi) * D128)[lane];
+            float4 v = reinterpret_cast<float4*>(xr)[lane];
+            v.x -= cv.x; v.y -= cv.y; v.z -= cv.z; v.w -= cv.w;
+            __syncwarp();
+            reinterpret_cast<float4*>(xr)[lane] = v;
+        }
+        __syncwarp();
+        for (int sub = lane; sub < m; sub += 32) {
+            const float* pc = pq + static_cast<int64_t>(sub) * PQ_KSUB * dsub;
+            float bd = FLT_MAX;
+            int bc = 0;
+            for (int c = 0; c < PQ_KSUB; ++c) {
+                float d = 0.f;
+                for (int j = 0; j < dsub; ++j) {
+                    const float t = xr[sub * dsub + j] - __ldg(pc + c * dsub + j);
+                    d += t * t;
+                }
+                if (d < bd) { bd = d; bc = c; }
+            }
+            codes[row * m + sub] = static_cast<uint8_t>(bc);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ inverted lists
+constexpr int SORT_CHUNK = 4096;     // rows per (single-warp) block of the stable counting sort
+
+__global__ void ivf_hist_kernel(const int32_t* __restrict__ assign, int64_t n, int nlist, int32_t* __restrict__ hist) {
+    // hist[list][chunk]; one warp per chunk
+    __shared__ int h[IVF_MAX_NLIST];
+    const int chunk = blockIdx.x, nchunks = gridDim.x;
+    for (int l = threadIdx.x; l < nlist; l += 32) h[l] = 0;
+    __syncwarp();
+    const int64_t lo = static_cast<int64_t>(chunk) * SORT_CHUNK;
+    const int64_t hi = lo + SORT_CHUNK < n ? lo + SORT_CHUNK : n;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 32) atomicAdd(&h[assign[i]], 1);
+    __syncwarp();
+    for (int l = threadIdx.x; l < nlist; l += 32) hist[static_cast<int64_t>(l) * nchunks + chunk] = h[l];
+}
+
+__global__ void ivf_scatter_kernel(const int32_t* __restrict__ assign, const uint8_t* __restrict__ codes, int64_t n,
+                                   int nlist, int m, const int64_t* __restrict__ base, uint8_t* __restrict__ lcodes,
+                                   int32_t* __restrict__ lids) {
+    // base[list][chunk] = first slot of this chunk's rows inside the list; rows keep their order (stable)
+    __shared__ int64_t run[IVF_MAX_NLIST];
+    const int chunk = blockIdx.x, nchunks = gridDim.x, lane = threadIdx.x;
+    for (int l = lane; l < nlist; l += 32) run[l] = base[static_cast<int64_t>(l) * nchunks + chunk];
+    __syncwarp();
+    const int64_t lo = static_cast<int64_t>(chunk) * SORT_CHUNK;
+    const int64_t hi = lo + SORT_CHUNK < n ? lo + SORT_CHUNK : n;
+    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const bool ok = i < hi;
+        const int l = ok ? assign[i] : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, l);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        int64_t pos = 0;
+        if (ok) pos = run[l] + rank;
+        __syncwarp();
+        if (ok && rank == __popc(peers) - 1) run[l] += __popc(peers);     // last peer advances the list cursor
+        __syncwarp();
+        if (ok) {
+            lids[pos] = static_cast<int32_t>(i);
+            const uint4* src = reinterpret_cast<const uint4*>(codes + i * m);
+            uint4* dst = reinterpret_cast<uint4*>(lcodes + pos * m);
+            for (int v = 0; v < m / 16; ++v) dst[v] = src[v];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ search
+// one warp per query row: the nprobe nearest coarse centroids, ascending (ties -> lower list id)
+__global__ void ivfpq_probe_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ coarse,
+                                   int nlist, int nprobe, int32_t* __restrict__ probes) {
+    __shared__ float qs[8][D128];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;
+    reinterpret_cast<float4*>(qs[w])[lane] = reinterpret_cast<const float4*>(q + i * D128)[lane];
+    __syncwarp();
+    float d[IVF_MAX_NLIST / 32];
+#pragma unroll
+    for (int t = 0; t < IVF_MAX_NLIST / 32; ++t) {
+        const int c = lane + 32 * t;
+        float acc = FLT_MAX;
+        if (c < nlist) {
+            acc = 0.f;
+            const float* cr = coarse + static_cast<int64_t>(c) * D128;
+            for (int j = 0; j < D128; ++j) {
+                const float v = qs[w][j] - __ldg(cr + j);
+                acc += v * v;
+            }
+        }
+        d[t] = acc;
+    }
+    for (int p = 0; p < nprobe; ++p) {
+        float best = FLT_MAX;
+        int bi = INT_MAX;
+#pragma unroll
+        for (int t = 0; t < IVF_MAX_NLIST / 32; ++t)
+            if (d[t] < best) { best = d[t]; bi = lane + 32 * t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) probes[i * nprobe + p] = bi == INT_MAX ? -1 : bi;
+#pragma unroll
+        for (int t = 0; t < IVF_MAX_NLIST / 32; ++t)
+            if (lane + 32 * t == bi) d[t] = FLT_MAX;
+    }
+}
+
+__device__ void block_sort_asc_u64(uint64_t* keys, int n) {
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = keys[i], b = keys[ixj];
+                    const bool asc = (i & k) == 0;
+                    if (asc ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// CTA (probe p, query row i): LUT T[m][c] = |(q - c_l)_m - pq_m[c]|^2 in shared memory, ADC scan of list l
+__global__ void __launch_bounds__(256)
+ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ coarse,
+                  const float* __restrict__ pq, int m, int dsub, const int32_t* __restrict__ probes, int nprobe,
+                  const uint8_t* __restrict__ lcodes, const int32_t* __restrict__ lids, const int32_t* __restrict__ loff,
+                  int k, int64_t label_offset, float* __restrict__ partD, int64_t* __restrict__ partI) {
+    extern __shared__ float lut[];                          // [m][256]
+    __shared__ uint64_t buf[IVF_SCAN_CAP];
+    __shared__ int cnt_s;
+    __shared__ unsigned long long thr_s;
+    const int p = blockIdx.x;
+    const int64_t i = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int l = probes[i * nprobe + p];
+    float* outD = partD + (static_cast<int64_t>(p) * nq + i) * k;
+    int64_t* outI = partI + (static_cast<int64_t>(p) * nq + i) * k;
+    const int64_t lo = l >= 0 ? loff[l] : 0, hi = l >= 0 ? loff[l + 1] : 0;
+    if (hi <= lo) {
+        for (int j = tid; j < k; j += blockDim.x) { outD[j] = INFINITY; outI[j] = -1; }
+        return;
+    }
+    for (int e = tid; e < m * PQ_KSUB; e += blockDim.x) {
+        const int sub = e >> 8, c = e & 255;
+        float d = 0.f;
+        for (int j = 0; j < dsub; ++j) {
+            const int dim = sub * dsub + j;
+            const float r = q[i * D128 + dim] - coarse[static_cast<int64_t>(l) * D128 + dim];
+            const float t = r - pq[(static_cast<int64_t>(sub) * PQ_KSUB + c) * dsub + j];
+            d += t * t;
+        }
+        lut[e] = d;
+    }
+    for (int e = tid; e < IVF_SCAN_CAP; e += blockDim.x) buf[e] = ~0ull;
+    if (tid == 0) { cnt_s = 0; thr_s = ~0ull; }
+    __syncthreads();
+    for (int64_t base = lo; base < hi; base += blockDim.x) {
+        const int64_t pos = base + tid;
+        if (pos < hi) {
+            const uint4* cp = reinterpret_cast<const uint4*>(lcodes + pos * m);
+            float d = 0.f;
+            for (int v = 0; v < m / 16; ++v) {
+                const uint4 cw = cp[v];
+                const uint32_t wds[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int sub = v * 16 + t * 4 + b;
+                        d += lut[sub * PQ_KSUB + ((wds[t] >> (8 * b)) & 255u)];
+                    }
+                }
+            }
+            const uint64_t key = (static_cast<uint64_t>(__float_as_uint(d)) << 32) | static_cast<uint32_t>(lids[pos]);
+            if (key < thr_s) {
+                const int slot = atomicAdd(&cnt_s, 1);
+                buf[slot] = key;         // slot < CAP: the buffer is pruned whenever fewer than 256 slots remain
+            }
+        }
+        __syncthreads();
+        if (cnt_s > IVF_SCAN_CAP - 256) {
+            block_sort_asc_u64(buf, IVF_SCAN_CAP);
+            for (int e = k + tid; e < IVF_SCAN_CAP; e += blockDim.x) buf[e] = ~0ull;
+            if (tid == 0) { cnt_s = k; thr_s = buf[k - 1]; }
+            __syncthreads();
+        }
+    }
+    block_sort_asc_u64(buf, IVF_SCAN_CAP);
+    for (int j = tid; j < k; j += blockDim.x) {
+        const uint64_t key = buf[j];
+        if (key != ~0ull) {
+            outD[j] = __uint_as_float(static_cast<uint32_t>(key >> 32));
+            outI[j] = static_cast<int64_t>(static_cast<uint32_t>(key)) + label_offset;
+        } else {
+            outD[j] = INFINITY;
+            outI[j] = -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits) {
+    NAFP_REQUIRE(nbits == 8, NAFP_ERR_UNSUPPORTED, "ivfpq: nbits=%d (only 8, as in the reference)", nbits);
+    NAFP_REQUIRE(nlist >= 1 && nlist <= IVF_MAX_NLIST, NAFP_ERR_INVALID, "ivfpq: nlist=%d outside [1,%d]", nlist, IVF_MAX_NLIST);
+    NAFP_REQUIRE(m >= 16 && m <= PQ_MAX_M && D128 % m == 0 && m % 16 == 0, NAFP_ERR_INVALID,
+                 "ivfpq: M=%d must divide 128 and be a multiple of 16 (<= 64)", m);
+    IvfPq* s = new IvfPq();
+    s->nlist = nlist;
+    s->m = m;
+    s->dsub = D128 / m;
+    NAFP_CUDA(cudaMalloc(&s->coarse, static_cast<size_t>(nlist) * D128 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->pq, static_cast<size_t>(m) * PQ_KSUB * s->dsub * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->loff, (nlist + 1) * sizeof(int32_t)));
+    idx->ivf = s;
+    return NAFP_OK;
+}
+
+void ivfpq_destroy(nafp_index* idx) {
+    IvfPq* s = idx->ivf;
+    if (!s) return;
+    void* bufs[] = {s->coarse, s->pq, s->assign, s->codes, s->lcodes, s->lids, s->loff, s->probes, s->partD, s->partI};
+    for (void* b : bufs) if (b) cudaFree(b);
+    delete s;
+    idx->ivf = nullptr;
+}
+
+int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
+    IvfPq* s = idx->ivf;
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    // faiss-style subsampling: at most 256 training points per centroid
+    const int64_t max_pts = 256ll * std::max(s->nlist, PQ_KSUB);
+    std::vector<int64_t> rows(n);
+    std::iota(rows.begin(), rows.end(), 0);
+    int64_t nt = n;
+    if (n > max_pts) {
+        std::mt19937_64 rng(static_cast<uint64_t>(seed));
+        for (int64_t i = 0; i < max_pts; ++i) {
+            std::uniform_int_distribution<int64_t> pick(i, n - 1);
+            std::swap(rows[i], rows[pick(rng)]);
+        }
+        nt = max_pts;
+        std::sort(rows.begin(), rows.begin() + nt);
+    }
+    std::vector<float> xt(static_cast<size_t>(nt) * D128);
+    for (int64_t i = 0; i < nt; ++i) memcpy(&xt[i * D128], x_host + rows[i] * D128, D128 * sizeof(float));
+    float *x_dev = nullptr, *r_dev = nullptr;
+    int32_t* a_dev = nullptr;
+    NAFP_CUDA(cudaMalloc(&x_dev, xt.size() * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&r_dev, xt.size() * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&a_dev, nt * sizeof(int32_t)));
+    NAFP_CUDA(cudaMemcpy(x_dev, xt.data(), xt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    NAFP_TRY(run_kmeans(ctx, x_dev, nt, D128, D128, s->nlist, s->coarse, a_dev, 25, static_cast<uint64_t>(seed) + 1));
+    // final assignment with the final centroids, then residuals
+    kmeans_assign_kernel<<<static_cast<unsigned>((nt + 7) / 8), 256, 8 * D128 * sizeof(float), ctx->stream>>>(
+        x_dev, nt, D128, D128, s->coarse, s->nlist, a_dev, nullptr);
+    residual_kernel<<<static_cast<unsigned>((nt * D128 + 255) / 256), 256, 0, ctx->stream>>>(x_dev, nt, s->coarse, a_dev, r_dev);
+    ctx->launches += 2;
+    for (int sub = 0; sub < s->m; ++sub)
+        NAFP_TRY(run_kmeans(ctx, r_dev + sub * s->dsub, nt, D128, s->dsub, PQ_KSUB,
+                            s->pq + static_cast<size_t>(sub) * PQ_KSUB * s->dsub, a_dev, 25,
+                            static_cast<uint64_t>(seed) + 2 + sub));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(x_dev);
+    cudaFree(r_dev);
+    cudaFree(a_dev);
+    s->trained = true;
+    return NAFP_OK;
+}
+
+int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
+    IvfPq* s = idx->ivf;
+    nafp_ctx* ctx = idx->ctx;
+    if (n == 0) return NAFP_OK;
+    if (idx->cap > s->cap) {
+        int32_t* a = nullptr;
+        uint8_t* c = nullptr;
+        NAFP_CUDA(cudaMalloc(&a, static_cast<size_t>(idx->cap) * sizeof(int32_t)));
+        NAFP_CUDA(cudaMalloc(&c, static_cast<size_t>(idx->cap) * s->m));
+        if (row0 > 0) {
+            NAFP_CUDA(cudaMemcpyAsync(a, s->assign, static_cast<size_t>(row0) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            NAFP_CUDA(cudaMemcpyAsync(c, s->codes, static_cast<size_t>(row0) * s->m, cudaMemcpyDeviceToDevice, ctx->stream));
+            NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        if (s->assign) cudaFree(s->assign);
+        if (s->codes) cudaFree(s->codes);
+        s->assign = a;
+        s->codes = c;
+        s->cap = idx->cap;
+    }
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    ivfpq_encode_kernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(idx->x32, row0, n, s->coarse, s->nlist, s->pq,
+                                                                              s->m, s->dsub, s->assign, s->codes);
+    ctx->launches++;
+    NAFP_CUDA(cudaGetLastError());
+    s->dirty = true;
+    return NAFP_OK;
+}
+
+static int build_lists(nafp_index* idx) {
+    IvfPq* s = idx->ivf;
+    nafp_ctx* ctx = idx->ctx;
+    const int64_t n = idx->n;
+    if (!s->dirty) return NAFP_OK;
+    if (s->sorted_cap < n) {
+        if (s->lcodes) cudaFree(s->lcodes);
+        if (s->lids) cudaFree(s->lids);
+        s->lcodes = nullptr; s->lids = nullptr; s->sorted_cap = 0;
+        NAFP_CUDA(cudaMalloc(&s->lcodes, static_cast<size_t>(idx->cap) * s->m));
+        NAFP_CUDA(cudaMalloc(&s->lids, static_cast<size_t>(idx->cap) * sizeof(int32_t)));
+        s->sorted_cap = idx->cap;
+    }
+    const int nchunks = static_cast<int>((n + SORT_CHUNK - 1) / SORT_CHUNK);
+    std::vector<int32_t> off(s->nlist + 1, 0);
+    if (nchunks > 0) {
+        int32_t* hist = nullptr;
+        int64_t* base = nullptr;
+        NAFP_CUDA(cudaMalloc(&hist, static_cast<size_t>(s->nlist) * nchunks * sizeof(int32_t)));
+        NAFP_CUDA(cudaMalloc(&base, static_cast<size_t>(s->nlist) * nchunks * sizeof(int64_t)));
+        ivf_hist_kernel<<<nchunks, 32, 0, ctx->stream>>>(s->assign, n, s->nlist, hist);
+        std::vector<int32_t> h(static_cast<size_t>(s->nlist) * nchunks);
+        NAFP_CUDA(cudaMemcpyAsync(h.data(), hist, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::vector<int64_t> b(h.size());
+        int64_t run = 0;
+        for (int l = 0; l < s->nlist; ++l) {
+            off[l] = static_cast<int32_t>(run);
+            for (int c = 0; c < nchunks; ++c) {
+                b[static_cast<size_t>(l) * nchunks + c] = run;
+                run += h[static_cast<size_t>(l) * nchunks + c];
+            }
+        }
+        off[s->nlist] = static_cast<int32_t>(run);
+        NAFP_CUDA(cudaMemcpyAsync(base, b.data(), b.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        ivf_scatter_kernel<<<nchunks, 32, 0, ctx->stream>>>(s->assign, s->codes, n, s->nlist, s->m, base, s->lcodes, s->lids);
+        ctx->launches += 2;
+        NAFP_CUDA(cudaGetLastError());
+        NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(hist);
+        cudaFree(base);
+    }
+    NAFP_CUDA(cudaMemcpy(s->loff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    s->dirty = false;
+    return NAFP_OK;
+}
+
+__global__ void topk_merge_kernel(const float* __restrict__ D_all, const int64_t* __restrict__ I_all, int W, int64_t nq,
+                                  int k, float* __restrict__ D_out, int64_t* __restrict__ I_out);
+
+int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    IvfPq* s = idx->ivf;
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "ivfpq search: index is not trained");
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    if (nq == 0) return NAFP_OK;
+    const int nprobe = idx->nprobe < s->nlist ? idx->nprobe : s->nlist;
+    NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
+                 "ivfpq search: need k <= %d and nprobe*k <= 2048 (nprobe %d, k %d)", MAX_K, nprobe, k);
+    NAFP_TRY(build_lists(idx));
+    const int64_t chunk = 4096;       // query rows per launch group (bounds the partial buffers)
+    if (s->scratch_nq < std::min(nq, chunk) || s->scratch_nprobe < nprobe || s->scratch_k < k) {
+        if (s->probes) cudaFree(s->probes);
+        if (s->partD) cudaFree(s->partD);
+        if (s->partI) cudaFree(s->partI);
+        s->probes = nullptr; s->partD = nullptr; s->partI = nullptr;
+        const int64_t cq = std::min(nq, chunk) > s->scratch_nq ? std::min(nq, chunk) : s->scratch_nq;
+        const int cp = nprobe > s->scratch_nprobe ? nprobe : s->scratch_nprobe;
+        const int ck = k > s->scratch_k ? k : s->scratch_k;
+        NAFP_CUDA(cudaMalloc(&s->probes, static_cast<size_t>(cq) * cp * sizeof(int32_t)));
+        NAFP_CUDA(cudaMalloc(&s->partD, static_cast<size_t>(cq) * cp * ck * sizeof(float)));
+        NAFP_CUDA(cudaMalloc(&s->partI, static_cast<size_t>(cq) * cp * ck * sizeof(int64_t)));
+        s->scratch_nq = cq; s->scratch_nprobe = cp; s->scratch_k = ck;
+    }
+    const size_t lut_bytes = static_cast<size_t>(s->m) * PQ_KSUB * sizeof(float);
+    NAFP_CUDA(cudaFuncSetAttribute(ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lut_bytes)));
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t nc = nq - q0 < chunk ? nq - q0 : chunk;
+        const float* qp = q_dev + q0 * D128;
+        ivfpq_probe_kernel<<<static_cast<unsigned>((nc + 7) / 8), 256, 0, ctx->stream>>>(qp, nc, s->coarse, s->nlist, nprobe, s->probes);
+        ivfpq_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, lut_bytes, ctx->stream>>>(
+            qp, nc, s->coarse, s->pq, s->m, s->dsub, s->probes, nprobe, s->lcodes, s->lids, s->loff, k, idx->label_offset,
+            s->partD, s->partI);
+        topk_merge_kernel<<<static_cast<unsigned>(nc), 128, 0, ctx->stream>>>(s->partD, s->partI, nprobe, nc, k, D_dev + q0 * k,
+                                                                              I_dev + q0 * k);
+        ctx->launches += 3;
+    }
+    NAFP_CUDA(cudaGetLastError());
+    idx->host_rows += nq;
+    return NAFP_OK;
+}
+
 }  // namespace nafp
 
-extern "C" int nafp_index_is_trained(nafp_index* idx) {
+using namespace nafp;
+
+extern "C" {
+
+int nafp_index_is_trained(nafp_index* idx) {
     if (!idx) return 0;
-    return idx->type == NAFP_INDEX_FLAT_L2 ? 1 : 0;
+    if (idx->type == NAFP_INDEX_FLAT_L2) return 1;
+    return idx->ivf && idx->ivf->trained ? 1 : 0;
 }
+
+int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_host) {
+    NAFP_REQUIRE(idx && idx->ivf && coarse_host && pq_host, NAFP_ERR_INVALID, "nafp_index_ivfpq_get_params: not an IVF-PQ index");
+    IvfPq* s = idx->ivf;
+    NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "nafp_index_ivfpq_get_params: index is not trained");
+    NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
+    NAFP_CUDA(cudaMemcpy(coarse_host, s->coarse, static_cast<size_t>(s->nlist) * D128 * sizeof(float), cudaMemcpyDeviceToHost));
+    NAFP_CUDA(cudaMemcpy(pq_host, s->pq, static_cast<size_t>(s->m) * PQ_KSUB * s->dsub * sizeof(float), cudaMemcpyDeviceToHost));
+    return NAFP_OK;
+}
+
+int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const float* pq_host) {
+    NAFP_REQUIRE(idx && idx->ivf && coarse_host && pq_host, NAFP_ERR_INVALID, "nafp_index_ivfpq_set_params: not an IVF-PQ index");
+    NAFP_REQUIRE(idx->n == 0, NAFP_ERR_STATE, "nafp_index_ivfpq_set_params: index already holds rows");
+    IvfPq* s = idx->ivf;
+    NAFP_CUDA(cudaMemcpy(s->coarse, coarse_host, static_cast<size_t>(s->nlist) * D128 * sizeof(float), cudaMemcpyHostToDevice));
+    NAFP_CUDA(cudaMemcpy(s->pq, pq_host, static_cast<size_t>(s->m) * PQ_KSUB * s->dsub * sizeof(float), cudaMemcpyHostToDevice));
+    s->trained = true;
+    return NAFP_OK;
+}
+
+}  // extern "C"

@@ -31,6 +31,7 @@ class Index:
         self.ctx = ctx or Context.get(device)
         self.d = int(d)
         self.index_type = index_type
+        self.nlist, self.pq_m = int(nlist), int(pq_m)
         h = ctypes.c_void_p()
         check(lib.nafp_index_create(self.ctx.h, int(index_type), int(d), int(nlist), int(pq_m), int(pq_nbits),
                                     ctypes.byref(h)))
@@ -64,6 +65,17 @@ class Index:
     def train(self, x, seed=1234):
         x = _f32c(x)
         check(lib.nafp_index_train(self.h, ptr(x), x.shape[0], int(seed)))
+
+    def ivfpq_params(self):
+        """(coarse (nlist,128), pq (M,256,128/M)) of a trained IVF-PQ index."""
+        coarse = np.empty((self.nlist, 128), np.float32)
+        pq = np.empty((self.pq_m, 256, 128 // self.pq_m), np.float32)
+        check(lib.nafp_index_ivfpq_get_params(self.h, ptr(coarse), ptr(pq)))
+        return coarse, pq
+
+    def set_ivfpq_params(self, coarse, pq):
+        coarse, pq = _f32c(coarse), _f32c(pq)
+        check(lib.nafp_index_ivfpq_set_params(self.h, ptr(coarse), ptr(pq)))
 
     def reserve(self, n_total):
         check(lib.nafp_index_reserve(self.h, int(n_total)))

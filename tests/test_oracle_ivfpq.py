@@ -1,0 +1,41 @@
+"""Oracle pinning, IVF-PQ: internal consistency of the numpy restatement."""
+import numpy as np
+
+from nafp_b200 import synth
+from oracle.flat_index import FlatL2
+from oracle.ivfpq_index import IVFPQ, kmeans
+
+
+def test_kmeans_objective_decreases_and_is_seeded():
+    x = synth.synth_fp_db(6000, seed=3)
+    c1, obj1 = kmeans(x, 32, niter=10, seed=5)
+    c2, _ = kmeans(x, 32, niter=10, seed=5)
+    assert (c1 == c2).all()
+    assert all(b <= a + 1e-3 for a, b in zip(obj1, obj1[1:]))
+    assert obj1[-1] < 0.9 * obj1[0]
+
+
+def test_ivfpq_recall_against_exact_search():
+    dummy, db, query = synth.synth_search_set(6000, 590, seed=4)
+    idx = IVFPQ(128, nlist=16, m=64)
+    idx.train(dummy)
+    idx.add(dummy)
+    idx.add(db)
+    idx.nprobe = 16                      # all lists: only the PQ approximation separates it from exact search
+    D, I = idx.search(query[:40], 20)
+    flat = FlatL2(128)
+    flat.add(dummy)
+    flat.add(db)
+    _, Ie = flat.search(query[:40], 20)
+    assert (I[:, 0] == Ie[:, 0]).mean() >= 0.9          # 64-byte codes on 128-d unit vectors are near-lossless for top-1
+    assert (np.diff(D, axis=1) >= 0).all() and (I >= 0).all()
+    idx.nprobe = 2
+    D2, I2 = idx.search(query[:40], 20)
+    assert 0.3 <= (I2[:, 0] == Ie[:, 0]).mean() <= (I[:, 0] == Ie[:, 0]).mean()   # fewer probes, lower recall
+    # labels are insertion order; -1 padding when the probed lists hold fewer than k rows
+    small = IVFPQ(128, nlist=16, m=64)
+    small.set_params(idx.coarse, idx.pq)
+    small.add(dummy[:5])
+    small.nprobe = 16
+    Ds, Is = small.search(query[:2], 20)
+    assert (Is[:, 5:] == -1).all() and np.isinf(Ds[:, 5:]).all() and set(Is[0, :5]) == set(range(5))
