@@ -1,7 +1,7 @@
 // Sequence-offset matcher: the body of the reference's evaluation hot loop
 // eval/eval_faiss.py:204-232, batched over test ids.
 //
-//   seq_gather_kernel   q rows of every test id (id .. id+L-1, zero rows past the end, :208)
+//   seq_gather_kernel   q rows of every test id (id .. id+L-1; rows past the end repeat the last one, :208)
 //   <segment search>    one top-k_probe search of all n_test*L rows (:211); rows of a shorter
 //                       sequence length are a prefix of the longest one, so one search serves all
 //   seq_cand_kernel     offset compensation (:215-216), sorted unique candidates >= 0 (:219) and,
@@ -29,9 +29,13 @@ __global__ void seq_gather_kernel(const float* __restrict__ qall, int64_t n_quer
     if (w >= n_test * L) return;
     const int64_t t = w / L;
     const int j = static_cast<int>(w % L);
-    const int64_t src = test_ids[t] + j;
+    // rows past the end of the query set (eval_faiss.py:208 truncates the slice) are never used by the
+    // matcher; they repeat the last real row so that the segment search does not see degenerate
+    // all-zero queries (every database row ties for those, which would force the exact fallback)
+    int64_t src = test_ids[t] + j;
+    if (src >= n_query_rows) src = n_query_rows - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (test_ids[t] >= 0 && src < n_query_rows) v = reinterpret_cast<const float4*>(qall + src * D128)[lane];
+    if (test_ids[t] >= 0 && test_ids[t] < n_query_rows) v = reinterpret_cast<const float4*>(qall + src * D128)[lane];
     reinterpret_cast<float4*>(qrows + w * D128)[lane] = v;
 }
 
