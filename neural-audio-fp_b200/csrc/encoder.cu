@@ -65,6 +65,7 @@ struct EncoderState {
     float* mel = nullptr;                      // (ENC_CHUNK, 256, 32) for the fused entry points
     void* xin = nullptr;                       // (ENC_CHUNK, 8000) staging for the *_host entry points
     float* emb = nullptr;                      // (ENC_CHUNK, 128)
+    float* raw = nullptr;                      // (ENC_CHUNK, 128) head outputs before the L2 normalisation
     CUtensorMap tmA[ENC_LAYERS], tmB[ENC_LAYERS];
     bool weights = false;
     int64_t last_n = 0;                        // segments of the last pass (activation probe)
@@ -115,52 +116,58 @@ static void build_geometry(ConvGeom* g) {
 __device__ __forceinline__ float elu(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
 
 // ------------------------------------------------------------------------------------------
-// conv0_a: (B,256,32) fp32 log-mel -> (B,256,16,128) fp16 pre-LN, stride 2 in time, pad (0,1)
-// one warp per output position, lane owns 4 channels
+// conv0_a: (B,256,32) fp32 log-mel -> (B,256,16,128) normalised fp16, stride 2 in time, pad (0,1).
+// K = 3: CUDA cores; fused with the log-mel max subtraction / clamp, bias, ELU and the LayerNorm
+// partial sums.  One warp per output position, lane owns 4 channels.  (A recompute variant --
+// statistics pass + apply pass, no pre-LN store -- measured slower: the ELU exponentials dominate.)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int64_t seg0,
-             int n_seg, const float* __restrict__ w0, const float* __restrict__ b0, __half* __restrict__ y,
-             float* __restrict__ part) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int seg = blockIdx.y;
-    if (seg >= n_seg) return;
+struct Conv0Lane {
     float w[3][4], bia[4];
+};
+__device__ __forceinline__ void conv0_load_lane(const float* __restrict__ w0, const float* __restrict__ b0, int lane,
+                                                Conv0Lane& L) {
 #pragma unroll
     for (int tap = 0; tap < 3; ++tap) {
         const float4 v = reinterpret_cast<const float4*>(w0 + tap * 128)[lane];
-        w[tap][0] = v.x; w[tap][1] = v.y; w[tap][2] = v.z; w[tap][3] = v.w;
+        L.w[tap][0] = v.x; L.w[tap][1] = v.y; L.w[tap][2] = v.z; L.w[tap][3] = v.w;
     }
-    {
-        const float4 v = reinterpret_cast<const float4*>(b0)[lane];
-        bia[0] = v.x; bia[1] = v.y; bia[2] = v.z; bia[3] = v.w;
+    const float4 v = reinterpret_cast<const float4*>(b0)[lane];
+    L.bia[0] = v.x; L.bia[1] = v.y; L.bia[2] = v.z; L.bia[3] = v.w;
+}
+// ELU(conv) of the lane's 4 channels at position p (= f * 16 + t') of one segment
+__device__ __forceinline__ void conv0_point(const float* __restrict__ m, int p, bool raw, float sub, const Conv0Lane& L,
+                                            float (&o)[4]) {
+    const int f = p >> 4, tp = p & 15;
+    float xv[3];
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+        const int t = 2 * tp + tap;
+        float v = t < 32 ? __ldg(m + f * 32 + t) : 0.f;
+        if (raw && t < 32) v = fmaxf(v - sub, -80.f);       // "- batch max, clamp -80" (melspectrogram.py:108-109)
+        xv[tap] = v;
     }
-    float sub = 0.f;
-    const bool raw = gmax != nullptr;     // raw log-mel: apply "- batch max, clamp -80" here (melspectrogram.py:108-109)
-    if (raw) sub = ord2f(gmax[(seg0 + seg) / group_size]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[c] = elu(L.bia[c] + xv[0] * L.w[0][c] + xv[1] * L.w[1][c] + xv[2] * L.w[2][c]);
+}
+
+__global__ void __launch_bounds__(256)
+conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int n_seg,
+             const float* __restrict__ w0, const float* __restrict__ b0, __half* __restrict__ y,
+             float* __restrict__ part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = blockIdx.y;
+    Conv0Lane L;
+    conv0_load_lane(w0, b0, lane, L);
+    const bool raw = gmax != nullptr;
+    const float sub = raw ? ord2f(gmax[seg / group_size]) : 0.f;
     const float* m = mel + static_cast<int64_t>(seg) * 8192;
     __half* out = y + static_cast<int64_t>(seg) * (256 * 16 * 128);
     float s1 = 0.f, s2 = 0.f;
-    // block handles 512 positions: blockIdx.x in [0, 8)
-    for (int p = blockIdx.x * 512 + warp; p < (blockIdx.x + 1) * 512; p += 8) {
-        const int f = p >> 4, tp = p & 15;
-        float xv[3];
-#pragma unroll
-        for (int tap = 0; tap < 3; ++tap) {
-            const int t = 2 * tp + tap;
-            float v = t < 32 ? m[f * 32 + t] : 0.f;
-            if (raw && t < 32) v = fmaxf(v - sub, -80.f);
-            xv[tap] = v;
-        }
+    for (int p = blockIdx.x * 512 + warp; p < (blockIdx.x + 1) * 512; p += 8) {      // 8 blocks x 512 positions
         float o[4];
+        conv0_point(m, p, raw, sub, L, o);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float a = bia[c] + xv[0] * w[0][c] + xv[1] * w[1][c] + xv[2] * w[2][c];
-            a = elu(a);
-            o[c] = a;
-            s1 += a;
-            s2 += a * a;
-        }
+        for (int c = 0; c < 4; ++c) { s1 += o[c]; s2 += o[c] * o[c]; }
         __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -384,78 +391,92 @@ ln_stats_kernel(const float* __restrict__ part, int slots, int n_seg, float* __r
 // ------------------------------------------------------------------------------------------
 // LayerNorm over (F,T,C) with per-element gamma/beta: 8 elements per thread
 // ------------------------------------------------------------------------------------------
+constexpr int LN_SEGS = 8;         // segments per thread: gamma/beta (8 B per element) are loaded once for all of them
 __global__ void __launch_bounds__(256)
 ln_apply_kernel(const __half* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, __half* __restrict__ x, int per_seg, int64_t total8) {
-    const int64_t i8 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i8 >= total8) return;
-    const int64_t idx = i8 * 8;
-    const int b = static_cast<int>(idx / per_seg);
-    const int off = static_cast<int>(idx % per_seg);
-    const float inv_n = 1.f / static_cast<float>(per_seg);
-    const float mean = stats[2 * b] * inv_n;
-    const float var = fmaxf(stats[2 * b + 1] * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + LN_EPS);
-    const uint4 raw = *reinterpret_cast<const uint4*>(y + idx);
-    const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+                const float* __restrict__ beta, __half* __restrict__ x, int per_seg, int n_seg) {
+    const int off = (blockIdx.x * blockDim.x + threadIdx.x) * 8;        // 8 consecutive elements of the (F,T,C) volume
+    if (off >= per_seg) return;
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + off), g1 = *reinterpret_cast<const float4*>(gamma + off + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(beta + off), b1 = *reinterpret_cast<const float4*>(beta + off + 4);
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint4 outv;
-    uint32_t* ov = reinterpret_cast<uint32_t*>(&outv);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hv[j]);
-        const float a = (f.x - mean) * rstd * gg[2 * j] + bb[2 * j];
-        const float c = (f.y - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1];
-        __half2 h = __floats2half2_rn(a, c);
-        ov[j] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(x + idx) = outv;
-}
-
-// ------------------------------------------------------------------------------------------
-// divide-and-encode head + L2 normalisation: one warp per segment, lane owns outputs 4 lane .. 4 lane + 3
-// x: (B, 1024) normalised fp16 (Flatten of (1,1,1024)); slice q = features 8q .. 8q+7 (nnfp.py:155)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-divenc_kernel(const __half* __restrict__ x, int n_seg, const float* __restrict__ w1, const float* __restrict__ b1,
-              const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ emb) {
-    const int lane = threadIdx.x & 31;
-    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (seg >= n_seg) return;
-    float out[4];
-    float ss = 0.f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int q = 4 * lane + r;
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(seg) * 1024 + q * 8);
+    const float inv_n = 1.f / static_cast<float>(per_seg);
+    const int seg0 = blockIdx.y * LN_SEGS;
+#pragma unroll 4
+    for (int k = 0; k < LN_SEGS; ++k) {
+        const int b = seg0 + k;
+        if (b >= n_seg) break;
+        const float mean = stats[2 * b] * inv_n;
+        const float var = fmaxf(stats[2 * b + 1] * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + LN_EPS);
+        const int64_t idx = static_cast<int64_t>(b) * per_seg + off;
+        const uint4 raw = *reinterpret_cast<const uint4*>(y + idx);
         const __half2* hv = reinterpret_cast<const __half2*>(&raw);
-        float in[8];
+        uint4 outv;
+        uint32_t* ov = reinterpret_cast<uint32_t*>(&outv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 f = __half22float2(hv[j]);
-            in[2 * j] = f.x;
-            in[2 * j + 1] = f.y;
+            const float a = (f.x - mean) * rstd * gg[2 * j] + bb[2 * j];
+            const float c = (f.y - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1];
+            __half2 h = __floats2half2_rn(a, c);
+            ov[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        float acc = b2[q];
-        const float* W1 = w1 + q * 8 * 32;     // (128, 8, 32)
-        for (int u = 0; u < 32; ++u) {
-            float hsum = b1[q * 32 + u];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) hsum += in[s] * W1[s * 32 + u];
-            hsum = hsum > 0.f ? hsum : expm1f(hsum);
-            acc += hsum * w2[q * 32 + u];
-        }
-        out[r] = acc;
-        ss += acc * acc;
+        *reinterpret_cast<uint4*>(x + idx) = outv;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// divide-and-encode head (nnfp.py:132-156): block (q, 128 segments) -- the 8x32 + 32 weights of slice q
+// sit in shared memory and are broadcast to the 128 segments; then one warp per segment L2-normalises.
+// x: (B, 1024) normalised fp16 (Flatten of (1,1,1024)); slice q = features 8q .. 8q+7 (nnfp.py:155)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+divenc_kernel(const __half* __restrict__ x, int n_seg, const float* __restrict__ w1, const float* __restrict__ b1,
+              const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ raw) {
+    __shared__ float W1[8 * 32], B1[32], W2[32];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < 256; i += 128) W1[i] = w1[q * 256 + i];
+    if (threadIdx.x < 32) {
+        B1[threadIdx.x] = b1[q * 32 + threadIdx.x];
+        W2[threadIdx.x] = w2[q * 32 + threadIdx.x];
+    }
+    __syncthreads();
+    const int seg = blockIdx.y * 128 + threadIdx.x;
+    if (seg >= n_seg) return;
+    const uint4 rv = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(seg) * 1024 + q * 8);
+    const __half2* hv = reinterpret_cast<const __half2*>(&rv);
+    float in[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hv[j]);
+        in[2 * j] = f.x;
+        in[2 * j + 1] = f.y;
+    }
+    float acc = b2[q];
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) {
+        float hsum = B1[u];
+#pragma unroll
+        for (int sdim = 0; sdim < 8; ++sdim) hsum += in[sdim] * W1[sdim * 32 + u];
+        hsum = hsum > 0.f ? hsum : expm1f(hsum);
+        acc += hsum * W2[u];
+    }
+    raw[static_cast<int64_t>(seg) * EMB + q] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+l2norm_kernel(const float* __restrict__ raw, int n_seg, float* __restrict__ emb) {
+    const int lane = threadIdx.x & 31;
+    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (seg >= n_seg) return;
+    const float4 v = reinterpret_cast<const float4*>(raw + static_cast<int64_t>(seg) * EMB)[lane];
+    float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = rsqrtf(fmaxf(ss, L2_EPS));
-    reinterpret_cast<float4*>(emb + static_cast<int64_t>(seg) * EMB)[lane] =
-        make_float4(out[0] * inv, out[1] * inv, out[2] * inv, out[3] * inv);
+    reinterpret_cast<float4*>(emb + static_cast<int64_t>(seg) * EMB)[lane] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
 }
 
 __global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
@@ -494,6 +515,7 @@ static int encoder_init(nafp_ctx* ctx) {
     NAFP_CUDA(cudaMalloc(&s->mel, static_cast<size_t>(ENC_CHUNK) * 8192 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->xin, static_cast<size_t>(ENC_CHUNK) * 8000 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->emb, static_cast<size_t>(ENC_CHUNK) * EMB * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->raw, static_cast<size_t>(ENC_CHUNK) * EMB * sizeof(float)));
     // tensor maps (activation maps are sized for ENC_CHUNK segments; rows past the live batch are masked)
     for (int l = 1; l < ENC_LAYERS; ++l) {
         const ConvGeom& L = s->g[l];
@@ -537,7 +559,7 @@ void encoder_destroy(nafp_ctx* ctx) {
         cudaFree(s->x[l]); cudaFree(s->bias[l]); cudaFree(s->ln_g[l]); cudaFree(s->ln_b[l]);
         if (s->wt[l]) cudaFree(s->wt[l]);
     }
-    void* bufs[] = {s->w0, s->y, s->stats, s->part, s->dw1, s->db1, s->dw2, s->db2, s->mel, s->xin, s->emb};
+    void* bufs[] = {s->w0, s->y, s->stats, s->part, s->raw, s->dw1, s->db1, s->dw2, s->db2, s->mel, s->xin, s->emb};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     ctx->encoder = nullptr;
@@ -552,33 +574,32 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
         const ConvGeom& L = s->g[l];
         float* stats = s->stats + static_cast<size_t>(l) * ENC_CHUNK * 2;
         const int per = L.ms * L.c_out;
-        int slots;
         if (l == 0) {
-            conv0_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, seg0, n, s->w0, s->bias[0], s->y, s->part);
-            slots = 64;
-        } else {
-            ConvParams p;
-            p.m_total = n * L.ms; p.ms = L.ms; p.c_in = L.c_in; p.c_out = L.c_out; p.nt = L.nt;
-            p.n_ntiles = L.c_out / L.nt; p.n_mtiles = (p.m_total + 127) / 128;
-            p.mode = L.mode; p.pad_lo = L.pad_lo; p.tap_lo = L.tap_lo; p.tap_hi = L.tap_hi;
-            p.kb_per_tap = L.c_in / 64; p.tps = L.ms >= 128 ? L.ms / 128 : 0; p.bf = L.bf; p.bb = L.bb;
-            p.groups = L.ms >= 32 ? L.ms / 32 : 1;
-            slots = p.groups * p.n_ntiles * 2;
-            const int tiles = p.n_mtiles * p.n_ntiles;
-            const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-            conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, s->part);
+            conv0_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, n, s->w0, s->bias[0], s->y, s->part);
+            ln_stats_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->part, 64, n, stats);
+            ln_apply_kernel<<<dim3((per / 8 + 255) / 256, (n + LN_SEGS - 1) / LN_SEGS), 256, 0, st>>>(
+                s->y, stats, s->ln_g[0], s->ln_b[0], s->x[0], per, n);
+            ctx->launches += 3;
+            continue;
         }
+        ConvParams p;
+        p.m_total = n * L.ms; p.ms = L.ms; p.c_in = L.c_in; p.c_out = L.c_out; p.nt = L.nt;
+        p.n_ntiles = L.c_out / L.nt; p.n_mtiles = (p.m_total + 127) / 128;
+        p.mode = L.mode; p.pad_lo = L.pad_lo; p.tap_lo = L.tap_lo; p.tap_hi = L.tap_hi;
+        p.kb_per_tap = L.c_in / 64; p.tps = L.ms >= 128 ? L.ms / 128 : 0; p.bf = L.bf; p.bb = L.bb;
+        p.groups = L.ms >= 32 ? L.ms / 32 : 1;
+        const int slots = p.groups * p.n_ntiles * 2;
+        const int tiles = p.n_mtiles * p.n_ntiles;
+        const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+        conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, s->part);
         ln_stats_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->part, slots, n, stats);
-        ctx->launches += 2;
-        if (l < ENC_LAYERS - 1 || true) {
-            const int64_t total8 = static_cast<int64_t>(n) * per / 8;
-            ln_apply_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, st>>>(s->y, stats, s->ln_g[l], s->ln_b[l],
-                                                                                      s->x[l], per, total8);
-            ctx->launches++;
-        }
+        ln_apply_kernel<<<dim3((per / 8 + 255) / 256, (n + LN_SEGS - 1) / LN_SEGS), 256, 0, st>>>(
+            s->y, stats, s->ln_g[l], s->ln_b[l], s->x[l], per, n);
+        ctx->launches += 3;
     }
-    divenc_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->x[ENC_LAYERS - 1], n, s->dw1, s->db1, s->dw2, s->db2, emb_dev);
-    ctx->launches++;
+    divenc_kernel<<<dim3(EMB, (n + 127) / 128), 128, 0, st>>>(s->x[ENC_LAYERS - 1], n, s->dw1, s->db1, s->dw2, s->db2, s->raw);
+    l2norm_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->raw, n, emb_dev);
+    ctx->launches += 2;
     NAFP_CUDA(cudaGetLastError());
     s->last_n = n;
     return NAFP_OK;

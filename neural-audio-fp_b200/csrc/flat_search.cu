@@ -906,7 +906,8 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
     NAFP_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h[0] > 0) {
-        const int kg_retry = grid_scan - 2 > kg ? grid_scan - 2 : kg;
+        // second chance: a threshold about one spread of the per-CTA maxima lower (~2x the survivors)
+        const int kg_retry = 2 * kg < grid_scan - 2 ? 2 * kg : (grid_scan - 2 > kg ? grid_scan - 2 : kg);
         for (int off = 0; off < h[0]; off += NQ_MAX) {
             const int np = h[0] - off < NQ_MAX ? h[0] - off : NQ_MAX;
             NAFP_TRY(scan_pass(idx, q_dev, list1, off, 0, np, k, kg_retry, grid_scan, n_tiles, n_search, list2, counts + 1,
