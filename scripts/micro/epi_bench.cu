@@ -1,0 +1,106 @@
+// Microbenchmark: cost of the scan epilogue's fast path (32 fp32 accumulators per lane from TMEM
+// compared against per-column thresholds) in several formulations, 1/2/4 warps per SM sub-partition.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../neural-audio-fp_b200/csrc/ptx.cuh"
+using namespace nafp;
+
+__device__ __forceinline__ float4 lds4(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds4nv(uint32_t a) { float4 v; asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+
+template <int V>
+__global__ void k(int reps, long long* out, int* sink, float hval) {
+    __shared__ uint32_t tbase;
+    __shared__ __align__(16) float thr[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) { tmem_alloc(&tbase, 512); tmem_relinquish(); }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) thr[i] = 1e30f;
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const float h = hval + lane * 1e-9f;
+    int hits = 0;
+    float treg[32];
+    if (V == 3) { for (int j = 0; j < 32; ++j) treg[j] = thr[j]; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+        const int c0 = (r * 32) & 255;
+        uint32_t v[32];
+        tmem_ld_32x32(base + c0, v);
+        tc_wait_ld();
+        const uint32_t ta = smem_u32(thr + c0);
+        bool p0 = false, p1 = false, p2 = false, p3 = false;
+        if (V == 0) {          // FADD + FSETP, volatile LDS
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) { const float4 t = lds4(ta + 16 * j4);
+                p0 |= (__uint_as_float(v[4*j4]) - h) > t.x; p1 |= (__uint_as_float(v[4*j4+1]) - h) > t.y;
+                p2 |= (__uint_as_float(v[4*j4+2]) - h) > t.z; p3 |= (__uint_as_float(v[4*j4+3]) - h) > t.w; }
+        } else if (V == 1) {   // FSETP only
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) { const float4 t = lds4(ta + 16 * j4);
+                p0 |= __uint_as_float(v[4*j4]) > t.x; p1 |= __uint_as_float(v[4*j4+1]) > t.y;
+                p2 |= __uint_as_float(v[4*j4+2]) > t.z; p3 |= __uint_as_float(v[4*j4+3]) > t.w; }
+        } else if (V == 2) {   // mixed ISETP / FSETP
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) { const float4 t = lds4(ta + 16 * j4);
+                p0 |= (int)v[4*j4] > __float_as_int(t.x); p1 |= __uint_as_float(v[4*j4+1]) > t.y;
+                p2 |= (int)v[4*j4+2] > __float_as_int(t.z); p3 |= __uint_as_float(v[4*j4+3]) > t.w; }
+        } else if (V == 3) {   // thresholds in registers, FSETP only
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                p0 |= __uint_as_float(v[j]) > treg[j]; p1 |= __uint_as_float(v[j+1]) > treg[j+1];
+                p2 |= __uint_as_float(v[j+2]) > treg[j+2]; p3 |= __uint_as_float(v[j+3]) > treg[j+3]; }
+        } else if (V == 4) {   // max-reduction: m = max(m, v - t) with 4 chains, non-volatile LDS
+            float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, m3 = -1e30f;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) { const float4 t = lds4nv(ta + 16 * j4);
+                m0 = fmaxf(m0, __uint_as_float(v[4*j4]) - t.x); m1 = fmaxf(m1, __uint_as_float(v[4*j4+1]) - t.y);
+                m2 = fmaxf(m2, __uint_as_float(v[4*j4+2]) - t.z); m3 = fmaxf(m3, __uint_as_float(v[4*j4+3]) - t.w); }
+            p0 = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > h;
+        } else if (V == 5) {   // integer max of raw bits vs integer thresholds: IMNMX chains (alu pipe only)
+            int m0 = INT_MIN, m1 = INT_MIN, m2 = INT_MIN, m3 = INT_MIN;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) { const float4 t = lds4nv(ta + 16 * j4);
+                m0 = max(m0, (int)v[4*j4] - __float_as_int(t.x)); m1 = max(m1, (int)v[4*j4+1] - __float_as_int(t.y));
+                m2 = max(m2, (int)v[4*j4+2] - __float_as_int(t.z)); m3 = max(m3, (int)v[4*j4+3] - __float_as_int(t.w)); }
+            p0 = max(max(m0, m1), max(m2, m3)) > 0;
+        } else if (V == 6) {   // no compare at all: just load (lower bound)
+            p0 = v[0] == 0x12345678u;
+        }
+        if (__any_sync(0xffffffffu, (p0 | p1) | (p2 | p3))) hits++;
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    if (lane == 0) out[blockIdx.x * 32 + warp] = t1 - t0;
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = hits;
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+template <int V> void run(const char* name, long long* out, int* sink) {
+    long long h[32];
+    for (int nt : {128, 256, 512}) {
+        const int reps = 512;
+        k<V><<<148, nt>>>(reps, out, sink, 0.5f);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("err %s\n", cudaGetErrorString(e)); return; }
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        double cyc = 0; for (int w = 0; w < nt / 32; ++w) cyc = h[w] > cyc ? h[w] : cyc;
+        printf("%-34s warps/SMSP %d: %7.1f cycles per 32-col chunk per warp, %6.1f cycles per chunk per SMSP\n", name, nt / 128,
+               cyc / reps, cyc / reps / (nt / 128));
+    }
+}
+
+int main() {
+    long long* out; int* sink;
+    cudaMalloc(&out, 148 * 32 * 8); cudaMalloc(&sink, 148 * 1024 * 4);
+    run<6>("V6 tcgen05.ld only", out, sink);
+    run<0>("V0 FADD+FSETP, LDS thr", out, sink);
+    run<1>("V1 FSETP only, LDS thr", out, sink);
+    run<2>("V2 ISETP/FSETP mixed, LDS thr", out, sink);
+    run<3>("V3 FSETP only, thr in registers", out, sink);
+    run<4>("V4 FADD+FMNMX max-reduce", out, sink);
+    run<5>("V5 IADD+IMNMX max-reduce", out, sink);
+    return 0;
+}
