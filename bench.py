@@ -293,13 +293,13 @@ def run_gpu(args):
 
     # ---- headline: resident
     sampler = ClockSampler(local_rank)
+    sampler.start()                       # nvidia-smi needs a few hundred ms to start; warm-up runs under load too
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize(dev)
     sidx.index.profile_scans(True)
     sidx.index.last_search_stats()
     launches0 = ctx.launches
-    sampler.start()
     ms_res = max_over_ranks(time_steps(torch, dev, step_resident, args.steps, 0, barrier))
     clocks = sampler.stop()
     launches = ctx.launches - launches0
