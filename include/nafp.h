@@ -193,18 +193,23 @@ int nafp_seq_match(nafp_index* idx, const float* q_host, int64_t n_query_rows,
  * GPUs (SURVEY §8 e): each rank searches its shard, the host all-gathers the per-rank top-k
  * (NCCL), nafp_topk_merge_dev merges them, every rank scores the candidates it owns
  * (-inf for the others), the host max-reduces the score tables, nafp_seq_top_dev picks the 10 best.
- *   qrows_dev        (n_test, max_len, d) gathered query rows (zero rows past the end of q)
- *   I_dev            (n_test*max_len, k_probe) merged global labels
+ *   rowmap_dev       (n_test*max_len) int32: row of the search-result table for (test id, offset), -1 past the end
+ *   uniq_rows_dev    the distinct query rows some (test id, offset) needs, ascending (capacity n_test*max_len)
+ *   I_dev            (n_uniq, k_probe) merged global labels of those rows
  *   cand_ids_dev     (n_test, 1024) int64 sorted unique candidate start ids, -1 padded
  *   cand_scores_dev  (n_test, n_len, 1024) float32, -inf where not a member / not owned
  *   n_cand_dev       (n_test) int32 */
-int nafp_seq_gather_dev(nafp_ctx* ctx, const float* q_dev, int64_t n_query_rows,
-                        const int64_t* test_ids_dev, int64_t n_test, int32_t max_len,
-                        float* qrows_dev);
-int nafp_seq_cand_dev(nafp_index* idx, const float* qrows_dev, int64_t n_query_rows,
+/* plan: overlapping query sequences share rows; each needed row is searched once.  scratch_dev holds
+ * 2*n_query_rows+1 int32.  Synchronises once to return the number of unique rows. */
+int nafp_seq_plan_dev(nafp_ctx* ctx, const int64_t* test_ids_dev, int64_t n_test, int32_t max_len,
+                      int64_t n_query_rows, int32_t* scratch_dev, int32_t* rowmap_dev,
+                      int32_t* uniq_rows_dev, int64_t* n_uniq_out);
+int nafp_seq_gather_rows_dev(nafp_ctx* ctx, const float* q_dev, const int32_t* rows_dev, int64_t n_rows,
+                             float* out_dev);
+int nafp_seq_cand_dev(nafp_index* idx, const float* q_dev, int64_t n_query_rows,
                       const int64_t* test_ids_dev, int64_t n_test, const int32_t* seq_lens_dev,
                       int32_t n_len, int32_t max_len, int32_t k_probe, const int64_t* I_dev,
-                      int64_t n_rows_global, int64_t owned_lo, int64_t owned_hi,
+                      const int32_t* rowmap_dev, int64_t n_rows_global, int64_t owned_lo, int64_t owned_hi,
                       int64_t* cand_ids_dev, float* cand_scores_dev, int32_t* n_cand_dev);
 int nafp_seq_top_dev(nafp_ctx* ctx, int64_t n_test, int32_t n_len, const int64_t* cand_ids_dev,
                      const float* cand_scores_dev, const int32_t* n_cand_dev,

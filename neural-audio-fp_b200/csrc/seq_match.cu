@@ -1,9 +1,10 @@
 // Sequence-offset matcher: the body of the reference's evaluation hot loop
 // eval/eval_faiss.py:204-232, batched over test ids.
 //
-//   seq_gather_kernel   q rows of every test id (id .. id+L-1; rows past the end repeat the last one, :208)
-//   <segment search>    one top-k_probe search of all n_test*L rows (:211); rows of a shorter
-//                       sequence length are a prefix of the longest one, so one search serves all
+//   seq_mark/scan/rowmap the UNIQUE query rows needed by the test ids (id .. id+L-1, truncated at the end
+//                       of the query set, :208): overlapping sequences share rows, each is searched once
+//   <segment search>    one top-k_probe search of the unique rows (:211); rows of a shorter sequence
+//                       length are a prefix of the longest one, so one search serves all lengths
 //   seq_cand_kernel     offset compensation (:215-216), sorted unique candidates >= 0 (:219) and,
 //                       per candidate, the running mean of q[j].recon[c+j] (:222-229) for every
 //                       requested length -- a gather/reduce over the fp32 rows
@@ -21,22 +22,73 @@ constexpr int SEQ_MAXC = 1024;     // k_probe * max_len upper bound
 constexpr int SEQ_MAXL = 32;
 constexpr int SEQ_NPRED = 10;
 
-__global__ void seq_gather_kernel(const float* __restrict__ qall, int64_t n_query_rows,
-                                  const int64_t* __restrict__ test_ids, int64_t n_test, int L,
-                                  float* __restrict__ qrows) {
+// ---- unique query rows: many test ids share rows (id .. id+L-1 overlap), each row is searched once
+__global__ void seq_mark_kernel(const int64_t* __restrict__ test_ids, int64_t n_test, int L, int64_t n_query_rows,
+                                int32_t* __restrict__ flags) {
+    const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= n_test * L) return;
+    const int64_t id = test_ids[w / L];
+    if (id < 0 || id >= n_query_rows) return;
+    int64_t r = id + static_cast<int>(w % L);
+    if (r >= n_query_rows) return;              // rows past the end are never used (eval_faiss.py:208 truncates)
+    flags[r] = 1;
+}
+// exclusive prefix sum of flags (single block, chunked); pos[r] = rank of row r among the marked rows
+__global__ void __launch_bounds__(1024)
+seq_scan_kernel(const int32_t* __restrict__ flags, int64_t n, int32_t* __restrict__ pos, int32_t* __restrict__ uniq_rows,
+                int32_t* __restrict__ n_uniq) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + tid;
+        const int f = i < n ? flags[i] : 0;
+        int x = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int s = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + x - f;
+        if (i < n) {
+            pos[i] = f ? excl : -1;
+            if (f) uniq_rows[excl] = static_cast<int32_t>(i);
+        }
+        __syncthreads();
+        if (tid == 0) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (tid == 0) *n_uniq = carry_s;
+}
+__global__ void seq_rowmap_kernel(const int64_t* __restrict__ test_ids, int64_t n_test, int L, int64_t n_query_rows,
+                                  const int32_t* __restrict__ pos, int32_t* __restrict__ rowmap) {
+    const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= n_test * L) return;
+    const int64_t id = test_ids[w / L];
+    const int64_t r = id + static_cast<int>(w % L);
+    rowmap[w] = (id >= 0 && r < n_query_rows) ? pos[r] : -1;
+}
+__global__ void seq_gather_rows_kernel(const float* __restrict__ qall, const int32_t* __restrict__ rows, int64_t n,
+                                       float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_test * L) return;
-    const int64_t t = w / L;
-    const int j = static_cast<int>(w % L);
-    // rows past the end of the query set (eval_faiss.py:208 truncates the slice) are never used by the
-    // matcher; they repeat the last real row so that the segment search does not see degenerate
-    // all-zero queries (every database row ties for those, which would force the exact fallback)
-    int64_t src = test_ids[t] + j;
-    if (src >= n_query_rows) src = n_query_rows - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (test_ids[t] >= 0 && test_ids[t] < n_query_rows) v = reinterpret_cast<const float4*>(qall + src * D128)[lane];
-    reinterpret_cast<float4*>(qrows + w * D128)[lane] = v;
+    if (w >= n) return;
+    reinterpret_cast<float4*>(out + w * D128)[lane] = reinterpret_cast<const float4*>(qall + static_cast<int64_t>(rows[w]) * D128)[lane];
 }
 
 __device__ void bitonic_sort_asc_1024(uint64_t* keys) {
@@ -59,9 +111,10 @@ __device__ void bitonic_sort_asc_1024(uint64_t* keys) {
 }
 
 __global__ void __launch_bounds__(256)
-seq_cand_kernel(const float* __restrict__ qrows, int64_t n_query_rows, const int64_t* __restrict__ test_ids,
+seq_cand_kernel(const float* __restrict__ qall, int64_t n_query_rows, const int64_t* __restrict__ test_ids,
                 const int32_t* __restrict__ seq_lens, int n_len, int L, int k_probe,
-                const int64_t* __restrict__ I, const float* __restrict__ x32, int64_t n_rows_local,
+                const int64_t* __restrict__ I, const int32_t* __restrict__ rowmap, const float* __restrict__ x32,
+                int64_t n_rows_local,
                 int64_t n_rows_global, int64_t label_offset, int64_t owned_lo, int64_t owned_hi,
                 int64_t* __restrict__ cand_ids, float* __restrict__ cand_scores, int32_t* __restrict__ n_cand) {
     __shared__ uint64_t keys[SEQ_MAXC];
@@ -80,7 +133,8 @@ seq_cand_kernel(const float* __restrict__ qrows, int64_t n_query_rows, const int
         if (e < L * k_probe) {
             const int j = e / k_probe, m = e % k_probe;
             if (j < lq) {
-                const int64_t lab = I[(t * L + j) * k_probe + m];
+                const int64_t irow = rowmap ? rowmap[t * L + j] : t * L + j;      // row of the search result table
+                const int64_t lab = I[irow * k_probe + m];
                 const int64_t c = lab - j;
                 if (lab >= 0 && c >= 0) key = (static_cast<uint64_t>(c) << 6) | static_cast<uint64_t>(j);
             }
@@ -116,7 +170,7 @@ seq_cand_kernel(const float* __restrict__ qrows, int64_t n_query_rows, const int
     for (int u = tid; u < SEQ_MAXC; u += blockDim.x) cand_ids[t * SEQ_MAXC + u] = u < nu ? uniq_c[u] : -1;
 
     // gather / reduce: per candidate the prefix sums of q[j] . recon[c + j]
-    const float* qt = qrows + t * L * D128;
+    const float* qt = qall + (lq > 0 ? id : 0) * D128;      // rows id .. id+lq-1 of the query set
     for (int u = warp; u < nu; u += 8) {
         const int64_t c = uniq_c[u];
         const bool owned = c >= owned_lo && c < owned_hi;
@@ -263,24 +317,50 @@ using namespace nafp;
 
 extern "C" {
 
-int nafp_seq_gather_dev(nafp_ctx* ctx, const float* q_dev, int64_t n_query_rows, const int64_t* test_ids_dev,
-                        int64_t n_test, int32_t max_len, float* qrows_dev) {
-    NAFP_REQUIRE(ctx && q_dev && test_ids_dev && qrows_dev && n_test >= 0 && max_len >= 1 && max_len <= SEQ_MAXL,
-                 NAFP_ERR_INVALID, "nafp_seq_gather_dev: bad arguments (max_len <= %d)", SEQ_MAXL);
-    if (n_test == 0) return NAFP_OK;
-    const int64_t warps = n_test * max_len;
-    seq_gather_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        q_dev, n_query_rows, test_ids_dev, n_test, max_len, qrows_dev);
+int nafp_seq_plan_dev(nafp_ctx* ctx, const int64_t* test_ids_dev, int64_t n_test, int32_t max_len,
+                      int64_t n_query_rows, int32_t* scratch_dev, int32_t* rowmap_dev, int32_t* uniq_rows_dev,
+                      int64_t* n_uniq_out) {
+    NAFP_REQUIRE(ctx && test_ids_dev && scratch_dev && rowmap_dev && uniq_rows_dev && n_uniq_out && n_test >= 0 &&
+                     max_len >= 1 && max_len <= SEQ_MAXL && n_query_rows >= 0 && n_query_rows < (1ll << 31),
+                 NAFP_ERR_INVALID, "nafp_seq_plan_dev: bad arguments (max_len <= %d)", SEQ_MAXL);
+    *n_uniq_out = 0;
+    if (n_test == 0 || n_query_rows == 0) return NAFP_OK;
+    int32_t* flags = scratch_dev;                        // [n_query_rows]
+    int32_t* pos = scratch_dev + n_query_rows;           // [n_query_rows]
+    int32_t* count = scratch_dev + 2 * n_query_rows;     // [1]
+    const int64_t pairs = n_test * max_len;
+    NAFP_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(n_query_rows) * sizeof(int32_t), ctx->stream));
+    seq_mark_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, ctx->stream>>>(test_ids_dev, n_test, max_len,
+                                                                                       n_query_rows, flags);
+    seq_scan_kernel<<<1, 1024, 0, ctx->stream>>>(flags, n_query_rows, pos, uniq_rows_dev, count);
+    seq_rowmap_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, ctx->stream>>>(test_ids_dev, n_test, max_len,
+                                                                                         n_query_rows, pos, rowmap_dev);
+    ctx->launches += 3;
+    NAFP_CUDA(cudaGetLastError());
+    int32_t h = 0;
+    NAFP_CUDA(cudaMemcpyAsync(&h, count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_uniq_out = h;
+    return NAFP_OK;
+}
+
+int nafp_seq_gather_rows_dev(nafp_ctx* ctx, const float* q_dev, const int32_t* rows_dev, int64_t n_rows,
+                             float* out_dev) {
+    NAFP_REQUIRE(ctx && n_rows >= 0 && (n_rows == 0 || (q_dev && rows_dev && out_dev)), NAFP_ERR_INVALID,
+                 "nafp_seq_gather_rows_dev: bad arguments");
+    if (n_rows == 0) return NAFP_OK;
+    seq_gather_rows_kernel<<<static_cast<unsigned>((n_rows * 32 + 255) / 256), 256, 0, ctx->stream>>>(q_dev, rows_dev, n_rows,
+                                                                                                    out_dev);
     ctx->launches++;
     NAFP_CUDA(cudaGetLastError());
     return NAFP_OK;
 }
 
-int nafp_seq_cand_dev(nafp_index* idx, const float* qrows_dev, int64_t n_query_rows, const int64_t* test_ids_dev,
+int nafp_seq_cand_dev(nafp_index* idx, const float* q_dev, int64_t n_query_rows, const int64_t* test_ids_dev,
                       int64_t n_test, const int32_t* seq_lens_dev, int32_t n_len, int32_t max_len, int32_t k_probe,
-                      const int64_t* I_dev, int64_t n_rows_global, int64_t owned_lo, int64_t owned_hi,
-                      int64_t* cand_ids_dev, float* cand_scores_dev, int32_t* n_cand_dev) {
-    NAFP_REQUIRE(idx && qrows_dev && test_ids_dev && seq_lens_dev && I_dev && cand_ids_dev && cand_scores_dev &&
+                      const int64_t* I_dev, const int32_t* rowmap_dev, int64_t n_rows_global, int64_t owned_lo,
+                      int64_t owned_hi, int64_t* cand_ids_dev, float* cand_scores_dev, int32_t* n_cand_dev) {
+    NAFP_REQUIRE(idx && q_dev && test_ids_dev && seq_lens_dev && I_dev && cand_ids_dev && cand_scores_dev &&
                      n_cand_dev, NAFP_ERR_INVALID, "nafp_seq_cand_dev: NULL argument");
     NAFP_REQUIRE(max_len >= 1 && max_len <= SEQ_MAXL && k_probe >= 1 && max_len * k_probe <= SEQ_MAXC &&
                      n_len >= 1 && n_len <= 32, NAFP_ERR_INVALID,
@@ -289,7 +369,7 @@ int nafp_seq_cand_dev(nafp_index* idx, const float* qrows_dev, int64_t n_query_r
     if (n_test == 0) return NAFP_OK;
     nafp_ctx* ctx = idx->ctx;
     seq_cand_kernel<<<static_cast<unsigned>(n_test), 256, 0, ctx->stream>>>(
-        qrows_dev, n_query_rows, test_ids_dev, seq_lens_dev, n_len, max_len, k_probe, I_dev, idx->x32, idx->n,
+        q_dev, n_query_rows, test_ids_dev, seq_lens_dev, n_len, max_len, k_probe, I_dev, rowmap_dev, idx->x32, idx->n,
         n_rows_global, idx->label_offset, owned_lo, owned_hi, cand_ids_dev, cand_scores_dev, n_cand_dev);
     ctx->launches++;
     NAFP_CUDA(cudaGetLastError());
@@ -337,16 +417,20 @@ int nafp_seq_match(nafp_index* idx, const float* q_host, int64_t n_query_rows, c
                  "nafp_seq_match: k_probe*max_len must be <= %d", SEQ_MAXC);
     nafp_ctx* ctx = idx->ctx;
     NAFP_CUDA(cudaSetDevice(ctx->device));
-    const int64_t rows = n_test * L;
+    const int64_t pairs = n_test * L;
+    const int64_t rows_cap = pairs < n_query_rows ? pairs : n_query_rows;      // unique query rows, at most
     // one arena for all temporaries
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_q = take(static_cast<size_t>(n_query_rows) * D128 * 4);
     const size_t o_ids = take(static_cast<size_t>(n_test) * 8);
     const size_t o_sl = take(static_cast<size_t>(n_len) * 4);
-    const size_t o_qrows = take(static_cast<size_t>(rows) * D128 * 4);
-    const size_t o_D = take(static_cast<size_t>(rows) * k_probe * 4);
-    const size_t o_I = take(static_cast<size_t>(rows) * k_probe * 8);
+    const size_t o_scr = take(static_cast<size_t>(2 * n_query_rows + 1) * 4);
+    const size_t o_map = take(static_cast<size_t>(pairs) * 4);
+    const size_t o_uniq = take(static_cast<size_t>(pairs) * 4);
+    const size_t o_qrows = take(static_cast<size_t>(rows_cap) * D128 * 4);
+    const size_t o_D = take(static_cast<size_t>(rows_cap) * k_probe * 4);
+    const size_t o_I = take(static_cast<size_t>(rows_cap) * k_probe * 8);
     const size_t o_cid = take(static_cast<size_t>(n_test) * SEQ_MAXC * 8);
     const size_t o_csc = take(static_cast<size_t>(n_test) * n_len * SEQ_MAXC * 4);
     const size_t o_nc = take(static_cast<size_t>(n_test) * 4);
@@ -357,6 +441,9 @@ int nafp_seq_match(nafp_index* idx, const float* q_host, int64_t n_query_rows, c
     float* q_dev = reinterpret_cast<float*>(base + o_q);
     int64_t* ids_dev = reinterpret_cast<int64_t*>(base + o_ids);
     int32_t* sl_dev = reinterpret_cast<int32_t*>(base + o_sl);
+    int32_t* scr = reinterpret_cast<int32_t*>(base + o_scr);
+    int32_t* rowmap = reinterpret_cast<int32_t*>(base + o_map);
+    int32_t* uniq = reinterpret_cast<int32_t*>(base + o_uniq);
     float* qrows = reinterpret_cast<float*>(base + o_qrows);
     float* Dd = reinterpret_cast<float*>(base + o_D);
     int64_t* Id = reinterpret_cast<int64_t*>(base + o_I);
@@ -368,10 +455,13 @@ int nafp_seq_match(nafp_index* idx, const float* q_host, int64_t n_query_rows, c
     NAFP_CUDA(cudaMemcpyAsync(q_dev, q_host, static_cast<size_t>(n_query_rows) * D128 * 4, cudaMemcpyHostToDevice, ctx->stream));
     NAFP_CUDA(cudaMemcpyAsync(ids_dev, test_ids, static_cast<size_t>(n_test) * 8, cudaMemcpyHostToDevice, ctx->stream));
     NAFP_CUDA(cudaMemcpyAsync(sl_dev, seq_lens, static_cast<size_t>(n_len) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    NAFP_TRY(nafp_seq_gather_dev(ctx, q_dev, n_query_rows, ids_dev, n_test, L, qrows));
-    NAFP_TRY(nafp_index_search_dev(idx, qrows, rows, k_probe, Dd, Id));
+    // every query row that some (test id, offset) needs is searched ONCE
+    int64_t n_uniq = 0;
+    NAFP_TRY(nafp_seq_plan_dev(ctx, ids_dev, n_test, L, n_query_rows, scr, rowmap, uniq, &n_uniq));
+    NAFP_TRY(nafp_seq_gather_rows_dev(ctx, q_dev, uniq, n_uniq, qrows));
+    NAFP_TRY(nafp_index_search_dev(idx, qrows, n_uniq, k_probe, Dd, Id));
     const int64_t n_search = idx->search_rows >= 0 && idx->search_rows < idx->n ? idx->search_rows : idx->n;
-    NAFP_TRY(nafp_seq_cand_dev(idx, qrows, n_query_rows, ids_dev, n_test, sl_dev, n_len, L, k_probe, Id,
+    NAFP_TRY(nafp_seq_cand_dev(idx, q_dev, n_query_rows, ids_dev, n_test, sl_dev, n_len, L, k_probe, Id, rowmap,
                                idx->label_offset + idx->n, idx->label_offset, idx->label_offset + n_search, cid, csc, nc));
     NAFP_TRY(nafp_seq_top_dev(ctx, n_test, n_len, cid, csc, nc, pid, psc));
     NAFP_CUDA(cudaMemcpyAsync(pred_ids_host, pid, static_cast<size_t>(n_test) * n_len * SEQ_NPRED * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -56,15 +56,30 @@ class TorchComm:
         return t
 
 
-def sharded_seq_match(ops, comm, qrows, test_ids, seq_lens, k_probe):
-    """Backend-agnostic orchestration; see the module docstring.  Returns (pred_ids, pred_scores)."""
-    D_loc, I_loc = ops.local_topk(qrows, k_probe)
-    D_all = comm.all_gather(D_loc)
-    I_all = comm.all_gather(I_loc)
-    _, I = ops.merge(D_all, I_all)
-    cand_ids, cand_scores, n_cand = ops.cand_scores(qrows, test_ids, seq_lens, k_probe, I)
-    cand_scores = comm.all_reduce_max(cand_scores)
+def sharded_seq_match(ops, comm, query, test_ids, seq_lens, k_probe):
+    """Backend-agnostic orchestration; see the module docstring.  ``query`` is the whole query set
+    (every rank holds it); returns (pred_ids, pred_scores)."""
+    plan = ops.plan(query, test_ids)               # unique query rows + (test id, offset) -> row map
+    D_loc, I_loc = ops.local_topk(plan.qrows, k_probe)
+    if comm is not None:
+        D_all = comm.all_gather(D_loc)
+        I_all = comm.all_gather(I_loc)
+        _, I = ops.merge(D_all, I_all)
+    else:
+        I = I_loc
+    cand_ids, cand_scores, n_cand = ops.cand_scores(query, plan, test_ids, seq_lens, k_probe, I)
+    if comm is not None:
+        cand_scores = comm.all_reduce_max(cand_scores)
     return ops.top(cand_ids, cand_scores, n_cand, len(seq_lens))
+
+
+class SeqPlan:
+    """Overlapping query sequences share rows: ``qrows`` (n_uniq, d) are the distinct query rows the
+    test ids need, ``rowmap`` (n_test*max_len) maps (test id, offset) to its row of ``qrows`` (-1 past
+    the end of the query set)."""
+
+    def __init__(self, qrows, rowmap, uniq_rows):
+        self.qrows, self.rowmap, self.uniq_rows = qrows, rowmap, uniq_rows
 
 
 class GpuOps:
@@ -90,12 +105,21 @@ class GpuOps:
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
 
-    def gather(self, q_dev, test_ids_dev):
+    def plan(self, q_dev, test_ids_dev):
+        t = self.torch
         n_test = test_ids_dev.numel()
-        qrows = self.torch.empty((n_test * self.max_len, 128), dtype=self.torch.float32, device=self.dev)
-        self.check(self.lib.nafp_seq_gather_dev(self.index.ctx.h, self._p(q_dev), self.n_query_rows, self._p(test_ids_dev),
-                                                n_test, self.max_len, self._p(qrows)))
-        return qrows
+        pairs = n_test * self.max_len
+        scratch = t.empty((2 * self.n_query_rows + 1,), dtype=t.int32, device=self.dev)
+        rowmap = t.empty((pairs,), dtype=t.int32, device=self.dev)
+        uniq = t.empty((max(pairs, 1),), dtype=t.int32, device=self.dev)
+        n_uniq = ctypes.c_int64(0)
+        self.check(self.lib.nafp_seq_plan_dev(self.index.ctx.h, self._p(test_ids_dev), n_test, self.max_len,
+                                              self.n_query_rows, self._p(scratch), self._p(rowmap), self._p(uniq),
+                                              ctypes.byref(n_uniq)))
+        n_uniq = int(n_uniq.value)
+        qrows = t.empty((n_uniq, 128), dtype=t.float32, device=self.dev)
+        self.check(self.lib.nafp_seq_gather_rows_dev(self.index.ctx.h, self._p(q_dev), self._p(uniq), n_uniq, self._p(qrows)))
+        return SeqPlan(qrows, rowmap, uniq[:n_uniq])
 
     def local_topk(self, qrows, k):
         n = qrows.shape[0]
@@ -111,13 +135,14 @@ class GpuOps:
         self.check(self.lib.nafp_topk_merge_dev(self.index.ctx.h, self._p(D_all), self._p(I_all), W, n, k, self._p(D), self._p(I)))
         return D, I
 
-    def cand_scores(self, qrows, test_ids_dev, seq_lens_dev, k, I):
+    def cand_scores(self, q_dev, plan, test_ids_dev, seq_lens_dev, k, I):
         n_test, n_len = test_ids_dev.numel(), seq_lens_dev.numel()
         cid = self.torch.empty((n_test, SEQ_MAXC), dtype=self.torch.int64, device=self.dev)
         csc = self.torch.empty((n_test, n_len, SEQ_MAXC), dtype=self.torch.float32, device=self.dev)
         nc = self.torch.empty((n_test,), dtype=self.torch.int32, device=self.dev)
-        self.check(self.lib.nafp_seq_cand_dev(self.index.h, self._p(qrows), self.n_query_rows, self._p(test_ids_dev), n_test,
-                                              self._p(seq_lens_dev), n_len, self.max_len, k, self._p(I), self.n_rows_global,
+        self.check(self.lib.nafp_seq_cand_dev(self.index.h, self._p(q_dev), self.n_query_rows, self._p(test_ids_dev), n_test,
+                                              self._p(seq_lens_dev), n_len, self.max_len, k, self._p(I),
+                                              self._p(plan.rowmap), self.n_rows_global,
                                               self.owned[0], self.owned[1], self._p(cid), self._p(csc), self._p(nc)))
         return cid, csc, nc
 
@@ -185,12 +210,8 @@ class ShardedFlatIndex:
     def seq_match_dev(self, q_dev, test_ids_dev, seq_lens_dev, k_probe=20):
         """Everything on device tensors (torch); returns device tensors."""
         ops = self.ops(q_dev.shape[0])
-        qrows = ops.gather(q_dev, test_ids_dev)
-        if self.world == 1 and self.comm is None:
-            D, I = ops.local_topk(qrows, k_probe)
-            cid, csc, nc = ops.cand_scores(qrows, test_ids_dev, seq_lens_dev, k_probe, I)
-            return ops.top(cid, csc, nc, seq_lens_dev.numel())
-        return sharded_seq_match(ops, self.comm, qrows, test_ids_dev, seq_lens_dev, k_probe)
+        comm = self.comm if (self.world > 1 or self.comm is not None) else None
+        return sharded_seq_match(ops, comm, q_dev, test_ids_dev, seq_lens_dev, k_probe)
 
     def seq_match(self, query, test_ids, seq_lens, k_probe=20):
         """Host arrays in, host arrays out (includes H2D / D2H)."""

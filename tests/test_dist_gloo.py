@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from nafp_b200 import synth
-from nafp_b200.dist import SEQ_MAXC, TorchComm, shard_with_halo, sharded_seq_match
+from nafp_b200.dist import SEQ_MAXC, SeqPlan, TorchComm, shard_with_halo, sharded_seq_match
 from oracle import seq_match
 from oracle.flat_index import FlatL2
 
@@ -31,13 +31,18 @@ class CpuOps:
         self.index = FlatL2(128)
         self.index.add(self.x[:self.hi - self.lo])         # halo rows are not searched
 
-    def gather(self, test_ids):
-        rows = np.zeros((len(test_ids) * MAX_LEN, 128), np.float32)
+    def plan(self, query, test_ids):
+        need = np.zeros(len(query), bool)
+        for i in test_ids:
+            need[i:i + MAX_LEN] = True
+        uniq = np.nonzero(need)[0]
+        pos = np.cumsum(need) - 1
+        rowmap = np.full(len(test_ids) * MAX_LEN, -1, np.int32)
         for t, i in enumerate(test_ids):
             for j in range(MAX_LEN):
-                if i + j < len(self.query):
-                    rows[t * MAX_LEN + j] = self.query[i + j]
-        return self.torch.from_numpy(rows)
+                if i + j < len(query):
+                    rowmap[t * MAX_LEN + j] = pos[i + j]
+        return SeqPlan(self.torch.from_numpy(query[uniq]), rowmap, uniq)
 
     def local_topk(self, qrows, k):
         D, I = self.index.search(qrows.numpy(), k)
@@ -52,9 +57,8 @@ class CpuOps:
         order = np.lexsort((np.where(I < 0, np.iinfo(np.int64).max, I), D), axis=1)[:, :k]
         return self.torch.from_numpy(np.take_along_axis(D, order, 1)), self.torch.from_numpy(np.take_along_axis(I, order, 1))
 
-    def cand_scores(self, qrows, test_ids, seq_lens, k, I):
-        q = qrows.numpy().reshape(len(test_ids), MAX_LEN, 128)
-        I = I.numpy().reshape(len(test_ids), MAX_LEN, k)
+    def cand_scores(self, query, plan, test_ids, seq_lens, k, I):
+        I = I.numpy()
         cid = np.full((len(test_ids), SEQ_MAXC), -1, np.int64)
         csc = np.full((len(test_ids), len(seq_lens), SEQ_MAXC), -np.inf, np.float32)
         nc = np.zeros(len(test_ids), np.int32)
@@ -62,7 +66,7 @@ class CpuOps:
             lq = min(MAX_LEN, len(self.query) - int(tid))
             cands = {}
             for j in range(lq):
-                for lab in I[t, j]:
+                for lab in I[plan.rowmap[t * MAX_LEN + j]]:
                     if lab >= 0 and lab - j >= 0:
                         cands[lab - j] = min(cands.get(lab - j, 99), j)
             keys = sorted(cands)
@@ -73,7 +77,7 @@ class CpuOps:
                     continue
                 avail = min(MAX_LEN, self.n_global - c, self.hi_halo - c)
                 terms = min(avail, lq)
-                d = [float(np.dot(q[t, j], self.x[c - self.lo + j])) for j in range(terms)]
+                d = [float(np.dot(query[int(tid) + j], self.x[c - self.lo + j])) for j in range(terms)]
                 for li, sl in enumerate(seq_lens):
                     m = min(sl, terms)
                     if m > 0 and cands[c] < min(sl, lq):
@@ -98,7 +102,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dummy, db, query = synth.synth_search_set(N_DUMMY, N_DB, seed=8)
     ops = CpuOps(np.concatenate([dummy, db]), rank, world, query)
-    pred, _ = sharded_seq_match(ops, TorchComm(), ops.gather(TEST_IDS), TEST_IDS, SEQ_LENS, K)
+    pred, _ = sharded_seq_match(ops, TorchComm(), query, TEST_IDS, SEQ_LENS, K)
     if rank == 0:
         np.save(out, pred)
     dist.barrier()
