@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int16, c_int32, c_int64,
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnafp.so")
+LIB_PATH = os.environ.get("NAFP_LIBRARY") or os.path.join(_HERE, "csrc", "libnafp.so")   # override: A/B builds
 
 
 class NafpError(RuntimeError):

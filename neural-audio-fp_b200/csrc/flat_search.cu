@@ -6,14 +6,16 @@
 // |q-x|^2), distance reported as |q|^2 - 2 s.
 //
 // One scan pass handles up to 256 query rows against the whole database:
-//   flat_prep_kernel    fp32 queries -> bf16 B-operand tile, |q|^2, pass state reset
-//   flat_scan_kernel    persistent, one CTA per SM, each CTA owns a contiguous run of 128-row DB
-//                       tiles: TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (M=128 DB rows,
-//                       N=queries, K=128, bf16, fp32 accumulators double-buffered in TMEM) ->
-//                       epilogue warps tcgen05.ld the accumulators, subtract 0.5|x|^2 and keep
-//                       only scores above a per-query threshold that all CTAs share through L2
-//                       (the kg-th largest of the per-CTA running maxima -- a valid lower bound on
-//                       the kg-th best score, maintained by one reducer warp per CTA, lock-free).
+//   flat_prep_kernel    fp32 queries -> bf16 A-operand tile, |q|^2, pass state reset
+//   flat_scan_kernel    persistent, one CTA per SM, each CTA owns a contiguous run of 256-row DB
+//                       tiles: TMA (SWIZZLE_128B) -> smem ring of K blocks -> tcgen05.mma (M = 128
+//                       queries, N = 256 DB rows, K = 128, bf16, fp32 accumulators double-buffered in
+//                       TMEM) -> epilogue threads own one query each: a 3-input max over the tile's
+//                       columns and ONE compare against  T + min_tile 0.5|x|^2 ; the rare columns
+//                       that pass get the exact  q.x - 0.5|x|^2 > T  test and join the CTA's pool.
+//                       T is a per-query threshold that all CTAs share through L2 (the kg-th largest
+//                       of the per-CTA running maxima -- a valid lower bound on the kg-th best
+//                       score, maintained by one reducer warp per CTA, lock-free).
 //   flat_select_kernel  per query: gather survivors, exact fp32 re-score, sort, and PROVE the
 //                       top-k: every dropped row has bf16 score <= T, hence exact score <= T + eps
 //                       with eps = (2u+u^2)|q|max|x| (u = 2^-8); if the k-th exact score is not
@@ -61,6 +63,23 @@ __global__ void flat_fill_kernel(float* hn, int64_t from, int64_t to, float v) {
     if (i < to) hn[i] = v;
 }
 
+// one warp per scan tile: min of 0.5|x|^2 over the tile's stored rows (the scan's prefilter offset)
+__global__ void flat_tile_hmin_kernel(const float* __restrict__ hn, float* __restrict__ tile_hmin, int64_t tile_first,
+                                      int64_t n_tiles, int64_t n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_tiles) return;
+    const int64_t t = tile_first + w;
+    float m = INFINITY;
+    for (int j = lane; j < SCAN_TILE; j += 32) {
+        const int64_t r = t * SCAN_TILE + j;
+        if (r < n_rows) m = fminf(m, hn[r]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) tile_hmin[t] = m;
+}
+
 // one warp per query row of the pass (rows >= nq are zero padding).  The pass takes rows
 // p0 .. p0+nq-1 of q_all, or -- for a retry pass -- the rows listed in src_list[src_off ..].
 __global__ void flat_prep_kernel(const float* __restrict__ q_all, const int32_t* __restrict__ src_list, int src_off,
@@ -97,20 +116,25 @@ __global__ void flat_prep_kernel(const float* __restrict__ q_all, const int32_t*
 // ------------------------------------------------------------------------------------------
 // the scan
 // ------------------------------------------------------------------------------------------
-constexpr int SCAN_STAGES = 4;
+constexpr int RING_SLOTS = 4;                           // K-block slots of the DB ring
 constexpr int EPI_WARPS = 16;
-constexpr int SCAN_THREADS = (3 + EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..17 epilogue, warp 18 reducer
-constexpr int EPI_PARTS = EPI_WARPS / 4;          // column interleave: warp takes every EPI_PARTS-th 32-query chunk
-constexpr int STAGE_BYTES = TILE_ROWS * D128 * 2;          // 32 KB: two 64-column K blocks of 16 KB
-constexpr int KBLOCK_BYTES = TILE_ROWS * 128;              // 16 KB
-constexpr int Q_BYTES_MAX = NQ_MAX * D128 * 2;             // 64 KB
-constexpr int SCAN_SMEM = Q_BYTES_MAX + SCAN_STAGES * STAGE_BYTES + (EPI_WARPS + 2) * NQ_MAX * 4 + 256 + 1024;
+constexpr int SCAN_THREADS = (3 + EPI_WARPS) * 32;   // warps 0..15 epilogue, 16 reducer, 17 TMA, 18 MMA (+TMEM alloc)
+constexpr int REDUCER_WARP = EPI_WARPS, TMA_WARP = EPI_WARPS + 1, MMA_WARP = EPI_WARPS + 2;   // the SM's warp arbiter
+                                                     // favours high warp ids: the MMA issuer must never wait for a slot
+constexpr int EPI_PARTS = EPI_WARPS / 4;          // the 4 warps of a TMEM lane quadrant split the tile's 256 DB rows
+constexpr int PART_COLS = SCAN_TILE / EPI_PARTS;  // 64 DB rows (accumulator columns) per warp per unit
+constexpr int SLOT_BYTES = SCAN_TILE * 128;                // 32 KB: one 64-column K block of a 256-row tile
+constexpr int BOX_BYTES = TILE_ROWS * 128;                 // 16 KB per TMA box (128 rows)
+constexpr int Q_KB_BYTES = NQ_MAX * 128;                   // 32 KB: one K block of the query operand
+constexpr int Q_BYTES_MAX = 2 * Q_KB_BYTES;                // 64 KB
+constexpr int SCAN_SMEM = Q_BYTES_MAX + RING_SLOTS * SLOT_BYTES + 2 * NQ_MAX * 4 + 256 + 1024;
 constexpr int NEG_INF_ORD = static_cast<int>(0x807FFFFFu);  // f2ord(-inf)
 constexpr int MAXONLY_CAP = 24;     // at most this many leading tiles are scanned max-only and re-scanned
+static_assert(PART_COLS == 64, "epilogue reads two 32-column chunks per unit");
 
 struct ScanBars {
-    uint64_t full[SCAN_STAGES];
-    uint64_t empty[SCAN_STAGES];
+    uint64_t full[RING_SLOTS];
+    uint64_t empty[RING_SLOTS];
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint64_t qfull;
@@ -128,22 +152,24 @@ __device__ __forceinline__ int smem_atom_inc(int* p) {
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
     return old;
 }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds_f1(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ int smem_ld_volatile(const int* p) {
     int v;
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
-// all four epilogue warps have fixed how many leading tiles they scanned max-only -> the maximum
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// lane 0 arrives; predicated instead of branched so the warp never diverges on the hot path
+__device__ __forceinline__ void mbar_arrive_lane0(uint64_t* bar, int lane) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(lane)
+        : "memory");
+}
+// all epilogue warps have fixed how many leading tiles they scanned max-only -> the maximum
 __device__ __forceinline__ int wait_redo_count(ScanBars* bars) {
     uint32_t spins = 0;
     while (smem_ld_volatile(&bars->decided) < EPI_WARPS) {
@@ -155,17 +181,34 @@ __device__ __forceinline__ int wait_redo_count(ScanBars* bars) {
     return r;
 }
 
+// one survivor of the prefilter: exact bf16 score against the exact threshold, then the CTA's pool
+__device__ __noinline__ void scan_append(float v, float t_exact, uint32_t row, uint32_t n_search, const float* __restrict__ hn,
+                                         int* cnt_q, int* lmax_q, uint64_t* pool_q) {
+    if (row >= n_search) return;                 // halo / padding rows never score
+    const float s = v - __ldg(hn + row);
+    if (s > t_exact) {
+        const int so = f2ord(s);
+        const int pos = smem_atom_inc(cnt_q);
+        if (pos < POOL_CAP) pool_q[pos] = (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
+        smem_red_max(lmax_q, so);
+    }
+}
+
+// Orientation: the MMA's M side (TMEM lanes) are the QUERIES, its N side (accumulator columns) the
+// DB rows of the tile.  An epilogue thread therefore owns one query per 128-query half: its
+// threshold is ONE register, and the hot loop is a 3-input max over the columns followed by a single
+// compare -- no per-score add, no threshold traffic.  -0.5|x|^2 enters the prefilter through the
+// tile's minimum (tile_hmin) and is applied exactly only to the few scores that pass it.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                 const float* __restrict__ hn, int64_t n_search, int n_tiles, int nq_pad, int kg,
-                 int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
+                 const float* __restrict__ hn, const float* __restrict__ tile_hmin, int64_t n_search, int n_tiles, int nq,
+                 int n_half, int kg, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
                  int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_s = smem;                                   // [2][nq_pad][128 B]
-    uint8_t* a_s = smem + Q_BYTES_MAX;                     // [stage][2][128][128 B]
-    float* thr_s = reinterpret_cast<float*>(a_s + SCAN_STAGES * STAGE_BYTES);   // [EPI_WARPS][NQ_MAX]
-    int* lmax_s = reinterpret_cast<int*>(thr_s + EPI_WARPS * NQ_MAX);
+    uint8_t* q_s = smem;                                   // [kb 2][256 query rows][128 B]
+    uint8_t* b_s = smem + Q_BYTES_MAX;                     // [slot][256 DB rows][128 B]
+    int* lmax_s = reinterpret_cast<int*>(b_s + RING_SLOTS * SLOT_BYTES);
     int* cnt_s = lmax_s + NQ_MAX;
     ScanBars* bars = reinterpret_cast<ScanBars*>(cnt_s + NQ_MAX);
 
@@ -176,11 +219,10 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int per = n_tiles / G, rem = n_tiles % G;
     const int t0 = cta * per + min(cta, rem);
     const int n_own = per + (cta < rem ? 1 : 0);
-    // Iterations 0..n_own-1 visit the CTA's tiles once.  Each epilogue warp scans its rows of the
-    // first R_w tiles "max-only" (no shared threshold exists yet, so it only feeds the running
-    // maxima); iterations n_own..n_own+R-1 (R = max R_w) re-visit those tiles with the threshold.
+    // Iterations 0..n_own-1 visit the CTA's tiles once.  Each epilogue warp scans the first R_w tiles
+    // "max-only" (no shared threshold exists yet, so it only feeds the running maxima); iterations
+    // n_own..n_own+R-1 (R = max R_w) re-visit those tiles with the threshold.
 
-    for (int i = threadIdx.x; i < EPI_WARPS * NQ_MAX; i += blockDim.x) thr_s[i] = -INFINITY;
     for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
         lmax_s[i] = INT_MIN;
         cnt_s[i] = 0;
@@ -188,7 +230,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_db);
-        for (int s = 0; s < SCAN_STAGES; ++s) {
+        for (int s = 0; s < RING_SLOTS; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
@@ -202,111 +244,132 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int w = 0; w < EPI_WARPS; ++w) bars->redo[w] = 0;
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);     // provably warp-uniform
 
-    if (warp == 0) {
+    if (warp == TMA_WARP) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->qfull, 2u * nq_pad * 128u);
+            const int q_rows = n_half * 128;
+            mbar_arrive_expect_tx(&bars->qfull, 2u * q_rows * 128u);
             for (int kb = 0; kb < 2; ++kb)
-                for (int r0 = 0; r0 < nq_pad; r0 += 32)
-                    tma_load_2d(q_s + kb * (nq_pad * 128) + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
+                for (int r0 = 0; r0 < q_rows; r0 += 32)
+                    tma_load_2d(q_s + kb * Q_KB_BYTES + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
             int n_iter = n_own;
             for (int i = 0; i < n_iter; ++i) {
-                const int s = i % SCAN_STAGES;
-                const uint32_t ph = (i / SCAN_STAGES) & 1;
-                mbar_wait_parked(&bars->empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
                 const int tile = t0 + (i < n_own ? i : i - n_own);
-                uint8_t* dst = a_s + s * STAGE_BYTES;
-                tma_load_2d(dst, &tmap_db, &bars->full[s], 0, tile * TILE_ROWS);
-                tma_load_2d(dst + KBLOCK_BYTES, &tmap_db, &bars->full[s], 64, tile * TILE_ROWS);
-                if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(1u, TILE_ROWS, static_cast<uint32_t>(nq_pad));
-            const uint32_t q_addr = smem_u32(q_s);
-            const uint32_t a_addr = smem_u32(a_s);
-            mbar_wait(&bars->qfull, 0);
-            int n_iter = n_own;
-            for (int i = 0; i < n_iter; ++i) {
-                const int s = i % SCAN_STAGES;
-                const uint32_t ph = (i / SCAN_STAGES) & 1;
-                const int acc = i & 1;
-                const uint32_t aph = (i >> 1) & 1;
-                mbar_wait_parked(&bars->tempty[acc], aph ^ 1);
-                mbar_wait_parked(&bars->full[s], ph);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * NQ_MAX;
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint64_t adesc = umma_desc_sw128(a_addr + s * STAGE_BYTES + kb * KBLOCK_BYTES + j * 32);
-                        const uint64_t bdesc = umma_desc_sw128(q_addr + kb * (nq_pad * 128) + j * 32);
-                        tc_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | j) != 0 ? 1u : 0u);
-                    }
+                    const int kc = 2 * i + kb;
+                    const int s = kc % RING_SLOTS;
+                    const uint32_t ph = (kc / RING_SLOTS) & 1;
+                    mbar_wait_parked(&bars->empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars->full[s], SLOT_BYTES);
+                    uint8_t* dst = b_s + s * SLOT_BYTES;
+                    tma_load_2d(dst, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE);
+                    tma_load_2d(dst + BOX_BYTES, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE + TILE_ROWS);
                 }
-                tc_commit(&bars->empty[s]);
-                tc_commit(&bars->tfull[acc]);
                 if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
             }
         }
         __syncwarp();
-    } else if (warp < 2 + EPI_WARPS) {
-        // ------------------------------------------------------------ epilogue (EPI_WARPS warps)
-        // Warp e reads TMEM lane quadrant (warp & 3) -- its 32 DB rows of the tile -- and takes every
-        // other 32-query chunk (half = e >> 2), so two warps per SM sub-partition hide each other's
-        // tcgen05.ld latency.  Each warp keeps a private copy of the thresholds of its own chunks.
-        const int qd = warp & 3;
-        const int e = warp - 2;           // 0..EPI_WARPS-1
-        const int half = e >> 2;          // column part 0..EPI_PARTS-1
-        constexpr int CSTEP = 32 * EPI_PARTS;        // distance between this warp's chunks
-        constexpr int NTHR = NQ_MAX / CSTEP;         // chunks (hence threshold registers) per warp
-        constexpr int QPW = NQ_MAX / EPI_WARPS;      // queries whose maxima this warp publishes
-        float* my_thr = thr_s + e * NQ_MAX;
-        int pub = INT_MIN;
-        int thr_ord[NTHR];
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------ MMA issuer
+        // unit = (tile, 128-query half): D[query][db row] in accumulator (unit & 1).  The second K block's
+        // slot is released as soon as the last unit's MMAs on it are issued, the first one's four MMAs earlier.
+        // The whole warp runs the loop (uniform control flow keeps descriptors and counters in uniform
+        // registers); one elected lane issues.
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc_f16(1u, 128u, static_cast<uint32_t>(SCAN_TILE));
+        const uint64_t adesc0 = umma_desc_sw128(smem_u32(q_s));
+        const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_s));
+        mbar_wait_parked(&bars->qfull, 0);
+        int n_iter = n_own;
+        uint32_t uc = 0;
+        for (int i = 0; i < n_iter; ++i) {
+            const int s0 = (2 * i) % RING_SLOTS, s1 = s0 + 1;
+            const uint32_t ph = ((2 * i) / RING_SLOTS) & 1;
+            for (int hq = 0; hq < n_half; ++hq, ++uc) {
+                const int acc = uc & 1;
+                const uint32_t aph = (uc >> 1) & 1;
+                const bool last = hq == n_half - 1;
+                mbar_wait_parked(&bars->tempty[acc], aph ^ 1);
+                if (hq == 0) mbar_wait_parked(&bars->full[s0], ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * SCAN_TILE;
+                const uint64_t a_kb0 = adesc0 + static_cast<uint64_t>((hq * (128 * 128)) >> 4);
+                const uint64_t a_kb1 = a_kb0 + static_cast<uint64_t>(Q_KB_BYTES >> 4);
+                const uint64_t b_kb0 = bdesc0 + static_cast<uint64_t>((s0 * SLOT_BYTES) >> 4);
+                const uint64_t b_kb1 = b_kb0 + static_cast<uint64_t>(SLOT_BYTES >> 4);
+                if (leader) {
 #pragma unroll
-        for (int r = 0; r < NTHR; ++r) thr_ord[r] = NEG_INF_ORD;
+                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, a_kb0 + 2 * j, b_kb0 + 2 * j, idesc, j != 0 ? 1u : 0u);
+                    if (last) tc_commit(&bars->empty[s0]);
+                }
+                if (hq == 0) {
+                    mbar_wait_parked(&bars->full[s1], ph);
+                    tc_fence_after();
+                }
+                if (leader) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, a_kb1 + 2 * j, b_kb1 + 2 * j, idesc, 1u);
+                    if (last) tc_commit(&bars->empty[s1]);
+                    tc_commit(&bars->tfull[acc]);
+                }
+                __syncwarp();
+            }
+            if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
+        }
+        __syncwarp();
+    } else if (warp < EPI_WARPS) {
+        // ------------------------------------------------------------ epilogue (EPI_WARPS warps)
+        // Warp e reads TMEM lane quadrant (warp & 3) -- 32 queries per half -- and the 64 accumulator
+        // columns (DB rows) [64 part, 64 part + 64) of every unit.
+        const int qd = warp & 3;
+        const int e = warp;               // 0..EPI_WARPS-1
+        const int part = e >> 2;          // 0..EPI_PARTS-1
+        constexpr int QPW = NQ_MAX / EPI_WARPS;      // queries whose maxima this warp publishes
+        const float NEG_INF = -INFINITY;
+        int pub = INT_MIN;
+        int thr_ord[2] = {NEG_INF_ORD, NEG_INF_ORD};
+        float t_exact[2], t_pre[2];       // exact threshold; same minus a rounding margin (prefilter base)
+        bool active[2];
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+            active[hq] = hq < n_half && (hq * 128 + qd * 32 + lane) < nq;
+            t_exact[hq] = active[hq] ? NEG_INF : INFINITY;      // padding queries never fire
+            t_pre[hq] = t_exact[hq];
+        }
         uint64_t* my_pool = pool + static_cast<int64_t>(cta) * NQ_MAX * POOL_CAP;
         bool normal = false;      // warp-uniform: thresholds of all of this warp's queries are known
         bool all_valid = false;
         int my_redo = 0;
         int n_iter = n_own;
-        // 0.5|x|^2 of this thread's row, prefetched one tile ahead (it is a cold DRAM read every tile)
-        auto load_h = [&](int it) -> float {
-            const int tl = t0 + (it >= n_own ? it - n_own : it);
-            const uint32_t rw = static_cast<uint32_t>(tl) * TILE_ROWS + qd * 32 + lane;
-            return (tl < n_tiles && rw < n_search) ? __ldg(hn + rw) : INFINITY;   // halo / padding rows never score
-        };
-        float h_next = load_h(0);
+        uint32_t uc = 0;
+        const uint32_t ns32 = static_cast<uint32_t>(n_search);
+        float hmin_next = n_own > 0 ? __ldg(tile_hmin + t0) : 0.f;
         for (int i = 0; i < n_iter; ++i) {
-            const int acc = i & 1;
-            const uint32_t aph = (i >> 1) & 1;
             const bool second_visit = i >= n_own;
             const int tile = t0 + (second_visit ? i - n_own : i);
-            const uint32_t row = static_cast<uint32_t>(tile) * TILE_ROWS + qd * 32 + lane;
-            const float h = h_next;
-            h_next = load_h(i + 1);
-            // shared thresholds of this warp's chunks: loads issued now, consumed after the tile
+            const float hmin_t = hmin_next;
+            {
+                const int inext = i + 1;
+                const int tnext = t0 + (inext >= n_own ? inext - n_own : inext);
+                hmin_next = tnext < n_tiles ? __ldg(tile_hmin + tnext) : 0.f;
+            }
+            // shared thresholds of this thread's queries: loads issued now, consumed after the tile
             const bool refresh = i < 12 || (i & 3) == 0 || i == n_own - 1;
-            int tg[NTHR];
+            int tg[2] = {INT_MIN, INT_MIN};
+            if (refresh) {
 #pragma unroll
-            for (int r = 0; r < NTHR; ++r) {
-                const int q = half * 32 + r * CSTEP + lane;
-                tg[r] = (refresh && q < nq_pad) ? ld_relaxed(&Tg[q]) : INT_MIN;
+                for (int hq = 0; hq < 2; ++hq)
+                    if (active[hq]) tg[hq] = ld_relaxed(&Tg[hq * 128 + qd * 32 + lane]);
             }
             if (!normal && ((i >= 1 && all_valid) || i >= MAXONLY_CAP)) {
                 normal = true;
@@ -316,96 +379,103 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     __threadfence_block();
                     smem_atom_inc(&bars->decided);
                 }
+                __syncwarp();
             }
             const bool maxonly = !normal;
             const bool skip = second_visit && (i - n_own) >= my_redo;     // this warp already scanned it normally
-            mbar_wait(&bars->tfull[acc], aph);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * NQ_MAX;
-            if (!skip) {
-                // one 32-column chunk: max-only tiles feed the running maxima, normal tiles keep the
-                // scores above the shared threshold (4 independent predicate chains, no serial OR)
-                auto process = [&](const uint32_t (&v)[32], int c0) {
+            const uint32_t row0 = static_cast<uint32_t>(tile) * SCAN_TILE + part * PART_COLS;
+            // prefilter: s = v - h > T  implies  v > T + min_tile(h) (minus a rounding margin)
+            const float hm = hmin_t * (1.f - 1.f / 1048576.f);
+            float hA = 0.f, hB = 0.f;
+            if (maxonly && !skip) {
+                const uint32_t ra = row0 + lane, rb = row0 + 32 + lane;
+                hA = ra < ns32 ? __ldg(hn + ra) : INFINITY;
+                hB = rb < ns32 ? __ldg(hn + rb) : INFINITY;
+            }
+            for (int hq = 0; hq < n_half; ++hq, ++uc) {
+                const int acc = uc & 1;
+                const uint32_t aph = (uc >> 1) & 1;
+                const int q = hq * 128 + qd * 32 + lane;
+                mbar_wait(&bars->tfull[acc], aph);
+                tc_fence_after();
+                if (!skip) {
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * SCAN_TILE + part * PART_COLS;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32(taddr, v0);
+                    tmem_ld_32x32(taddr + 32, v1);
+                    tc_wait_ld();
                     if (maxonly) {
+                        float m = NEG_INF;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(v[j]) - h;
-                            const int m = __reduce_max_sync(0xffffffffu, f2ord(s));
-                            if (lane == j) smem_red_max(&lmax_s[c0 + j], m);
+                            m = fmaxf(m, __uint_as_float(v0[j]) - __shfl_sync(0xffffffffu, hA, j));
+                            m = fmaxf(m, __uint_as_float(v1[j]) - __shfl_sync(0xffffffffu, hB, j));
                         }
+                        if (hq == 0 ? active[0] : active[1]) smem_red_max(&lmax_s[q], f2ord(m));
                     } else {
-                        bool p0 = false, p1 = false, p2 = false, p3 = false;
-                        const uint32_t thr_addr = smem_u32(my_thr + c0);
+                        float ma = __uint_as_float(v0[0]), mb = __uint_as_float(v1[0]);
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 t4 = lds_f4(thr_addr + 16 * j4);
-                            p0 |= (__uint_as_float(v[4 * j4 + 0]) - h) > t4.x;
-                            p1 |= (__uint_as_float(v[4 * j4 + 1]) - h) > t4.y;
-                            p2 |= (__uint_as_float(v[4 * j4 + 2]) - h) > t4.z;
-                            p3 |= (__uint_as_float(v[4 * j4 + 3]) - h) > t4.w;
+                        for (int j = 1; j < 31; j += 2) {
+                            ma = fmax3(ma, __uint_as_float(v0[j]), __uint_as_float(v0[j + 1]));
+                            mb = fmax3(mb, __uint_as_float(v1[j]), __uint_as_float(v1[j + 1]));
                         }
-                        // rare: some lane beat a threshold.  Only the column classes (j mod 4) that fired are re-scanned.
-                        const bool pr[4] = {p0, p1, p2, p3};
+                        ma = fmax3(ma, mb, __uint_as_float(v0[31]));
+                        ma = fmaxf(ma, __uint_as_float(v1[31]));
+                        const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
+                        const bool fired = ma > tp;
+                        if (__any_sync(0xffffffffu, fired)) {
+                            // rare: this lane's query has a score above the prefilter among the 64 columns
+                            if (fired) {
+                                const float te = hq == 0 ? t_exact[0] : t_exact[1];
+                                int* cq = &cnt_s[q];
+                                int* lq = &lmax_s[q];
+                                uint64_t* pq = my_pool + q * POOL_CAP;
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (__any_sync(0xffffffffu, pr[r])) {
+                                for (int j = 0; j < 32; ++j)
+                                    if (__uint_as_float(v0[j]) > tp) scan_append(__uint_as_float(v0[j]), te, row0 + j, ns32, hn, cq, lq, pq);
 #pragma unroll
-                                for (int j4 = 0; j4 < 8; ++j4) {
-                                    const int j = 4 * j4 + r;
-                                    const float s = __uint_as_float(v[j]) - h;
-                                    if (s > lds_f1(thr_addr + 4 * j)) {
-                                        const int so = f2ord(s);
-                                        const int pos = smem_atom_inc(&cnt_s[c0 + j]);
-                                        if (pos < POOL_CAP)
-                                            my_pool[(c0 + j) * POOL_CAP + pos] =
-                                                (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
-                                        smem_red_max(&lmax_s[c0 + j], so);
-                                    }
-                                }
+                                for (int j = 0; j < 32; ++j)
+                                    if (__uint_as_float(v1[j]) > tp)
+                                        scan_append(__uint_as_float(v1[j]), te, row0 + 32 + j, ns32, hn, cq, lq, pq);
                             }
+                            __syncwarp();
                         }
                     }
-                };
-                // 4 warps per SM sub-partition hide each other's tcgen05.ld / dependency latencies
-                for (int c0 = half * 32; c0 < nq_pad; c0 += CSTEP) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c0, v);
-                    tc_wait_ld();
-                    process(v, c0);
                 }
+                tc_fence_before();
+                __syncwarp();
+                mbar_arrive_lane0(&bars->tempty[acc], lane);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tempty[acc]);
-            // publish this CTA's running maxima: warp e owns queries [QPW e, QPW e + QPW)
-            {
-                const int q = e * QPW + lane;
-                if (lane < QPW && q < nq_pad) {
-                    const int m = smem_ld_volatile(&lmax_s[q]);
-                    if (m > pub) {
-                        st_relaxed(&Mx[q * G + cta], m);
-                        pub = m;
+            if (refresh) {
+                // publish this CTA's running maxima: warp e owns queries [QPW e, QPW e + QPW)
+                {
+                    const int q = e * QPW + lane;
+                    if (lane < QPW && q < nq) {
+                        const int m = smem_ld_volatile(&lmax_s[q]);
+                        if (m > pub) {
+                            st_relaxed(&Mx[q * G + cta], m);
+                            pub = m;
+                        }
                     }
                 }
-            }
-            // consume the threshold loads issued at the top of the iteration
-            if (refresh) {
+                // consume the threshold loads issued at the top of the iteration
                 bool valid = true;
 #pragma unroll
-                for (int r = 0; r < NTHR; ++r) {
-                    const int q = half * 32 + r * CSTEP + lane;
-                    if (q < nq_pad) {
-                        if (tg[r] > thr_ord[r]) {
-                            if (dbg_first && qd == 0 && thr_ord[r] == NEG_INF_ORD) dbg_first[cta * NQ_MAX + q] = i;
-                            thr_ord[r] = tg[r];
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(my_thr + q)), "f"(ord2f(tg[r])) : "memory");
+                for (int hq = 0; hq < 2; ++hq) {
+                    if (active[hq]) {
+                        if (tg[hq] > thr_ord[hq]) {
+                            if (dbg_first && part == 0 && thr_ord[hq] == NEG_INF_ORD)
+                                dbg_first[cta * NQ_MAX + hq * 128 + qd * 32 + lane] = i;
+                            thr_ord[hq] = tg[hq];
+                            const float t = ord2f(tg[hq]);
+                            t_exact[hq] = t;
+                            t_pre[hq] = t - fabsf(t) * (1.f / 1048576.f) - 1e-37f;
                         }
-                        valid = valid && (thr_ord[r] > NEG_INF_ORD);
+                        valid = valid && (thr_ord[hq] > NEG_INF_ORD);
                     }
                 }
                 all_valid = __all_sync(0xffffffffu, valid);
             }
-            __syncwarp();
             if (i == n_own - 1) {
                 if (!normal) {       // thresholds never arrived: everything is re-scanned (tiny databases)
                     normal = true;
@@ -415,6 +485,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         __threadfence_block();
                         smem_atom_inc(&bars->decided);
                     }
+                    __syncwarp();
                 }
                 n_iter = n_own + wait_redo_count(bars);
             }
@@ -424,7 +495,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         {
             const int q = e * QPW + lane;
-            if (lane < QPW && q < nq_pad) {
+            if (lane < QPW && q < nq) {
                 const int c = cnt_s[q];
                 cnt[cta * NQ_MAX + q] = min(c, POOL_CAP);
                 if (c > POOL_CAP) flags[q] = 1;      // pool overflow -> exact fallback answers this query
@@ -435,8 +506,11 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // ------------------------------------------------------------ threshold reducer (last warp)
         // For the queries assigned to this CTA: T = kg-th largest of the per-CTA maxima.  At least kg
         // distinct rows score >= T, so dropping rows that score <= T can never lose a top-kg row.
+        // The thresholds converge within the first few dozen tiles; afterwards the select runs rarely so
+        // that this warp stops competing for its sub-partition's issue slots.
+        uint32_t round = 0;
         while (smem_ld_volatile(&bars->done) < EPI_WARPS) {
-            for (int q = cta; q < nq_pad; q += G) {
+            for (int q = cta; q < nq; q += G) {
                 uint32_t u[5];
 #pragma unroll
                 for (int t = 0; t < 5; ++t) {
@@ -456,13 +530,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int T = static_cast<int>(res ^ 0x80000000u);
                 if (lane == 0 && T > NEG_INF_ORD && T > ld_relaxed(&Tg[q])) st_relaxed(&Tg[q], T);
             }
-            __nanosleep(100);
+            ++round;
+            __nanosleep(round < 48 ? 100 : (round < 96 ? 1000 : 4000));
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -737,6 +812,8 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     float* x32 = nullptr;
     __nv_bfloat16* x16 = nullptr;
     float* hn = nullptr;
+    float* tile_hmin = nullptr;
+    NAFP_CUDA(cudaMalloc(&tile_hmin, static_cast<size_t>(new_cap / SCAN_TILE + 2) * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&x32, static_cast<size_t>(new_cap) * idx->d * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&x16, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16)));
     NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap) * sizeof(float)));
@@ -747,6 +824,8 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
         NAFP_CUDA(cudaMemcpyAsync(x16, idx->x16, static_cast<size_t>(idx->n) * idx->d * sizeof(__nv_bfloat16),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
         NAFP_CUDA(cudaMemcpyAsync(hn, idx->hn, static_cast<size_t>(idx->n) * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        NAFP_CUDA(cudaMemcpyAsync(tile_hmin, idx->tile_hmin, static_cast<size_t>((idx->n + SCAN_TILE - 1) / SCAN_TILE) * sizeof(float),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     }
     {
@@ -761,6 +840,8 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     if (idx->x32) cudaFree(idx->x32);
     if (idx->x16) cudaFree(idx->x16);
     if (idx->hn) cudaFree(idx->hn);
+    if (idx->tile_hmin) cudaFree(idx->tile_hmin);
+    idx->tile_hmin = tile_hmin;
     idx->x32 = x32;
     idx->x16 = x16;
     idx->hn = hn;
@@ -791,7 +872,12 @@ int flat_add_dev(nafp_index* idx, const float* x, int64_t n, bool src_is_host) {
     if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
     flat_convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(idx->x32, idx->x16, idx->hn,
                                                                                         idx->maxn2, idx->n, n);
-    ctx->launches++;
+    {
+        const int64_t tf = idx->n / SCAN_TILE, tl = (idx->n + n - 1) / SCAN_TILE;
+        flat_tile_hmin_kernel<<<static_cast<unsigned>(((tl - tf + 1) * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
+            idx->hn, idx->tile_hmin, tf, tl - tf + 1, idx->n + n);
+    }
+    ctx->launches += 2;
     NAFP_CUDA(cudaGetLastError());
     if (src_is_host) NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     idx->n += n;
@@ -845,14 +931,15 @@ static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_lis
                      int kg, int grid_scan, int n_tiles, int64_t n_search, int32_t* fail_list, int32_t* fail_count,
                      float* D_dev, int64_t* I_dev) {
     nafp_ctx* ctx = idx->ctx;
-    const int nq_pad = (np + 31) / 32 * 32;
+    const int n_half = np > 128 ? 2 : 1;
+    const int nq_pad = n_half * 128;
     flat_prep_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, ctx->stream>>>(q_dev, src_list, src_off, p0, np, nq_pad, grid_scan,
                                                                          idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
                                                                          idx->flags, idx->gidx);
     const bool prof = idx->profile && idx->prof_n < PROF_RING;
     if (prof) cudaEventRecord(idx->prof_ev[2 * idx->prof_n], ctx->stream);
-    flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, n_search, n_tiles,
-                                                                          nq_pad, kg, idx->Mx, idx->Tg, idx->pool, idx->cnt,
+    flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, idx->tile_hmin, n_search,
+                                                                          n_tiles, np, n_half, kg, idx->Mx, idx->Tg, idx->pool, idx->cnt,
                                                                           idx->flags, idx->dbg_first);
     if (prof) {
         cudaEventRecord(idx->prof_ev[2 * idx->prof_n + 1], ctx->stream);
@@ -878,7 +965,7 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
     NAFP_TRY(ensure_scratch(idx));
     if (nq == 0) return NAFP_OK;
     const int64_t n_search = (idx->search_rows >= 0 && idx->search_rows < idx->n) ? idx->search_rows : idx->n;
-    const int n_tiles = static_cast<int>((n_search + TILE_ROWS - 1) / TILE_ROWS);
+    const int n_tiles = static_cast<int>((n_search + SCAN_TILE - 1) / SCAN_TILE);
     const int kg = k + 28;
     const int grid_scan = n_tiles < idx->grid ? (n_tiles > 0 ? n_tiles : 1) : idx->grid;
     const bool brute = (n_search < 8192) || (kg > grid_scan) || (k > 64);
@@ -963,7 +1050,7 @@ int nafp_index_destroy(nafp_index* idx) {
     cudaStreamSynchronize(idx->ctx->stream);
     if (idx->ivf) ivfpq_destroy(idx);
     for (auto& e : idx->prof_ev) cudaEventDestroy(e);
-    void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
+    void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->tile_hmin, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
                     idx->pool, idx->cnt, idx->flags, idx->gidx, idx->fail_list, idx->brute_part, idx->stats, idx->dbg_first, idx->stage_q, idx->stage_D,
                     idx->stage_I};
     for (void* b : bufs)

@@ -9,8 +9,9 @@
 namespace nafp {
 
 constexpr int D128 = 128;            // fingerprint dimension the tensor-core scan is built for
-constexpr int NQ_MAX = 256;          // query rows per scan pass (MMA N)
-constexpr int TILE_ROWS = 128;       // DB rows per MMA tile (MMA M)
+constexpr int NQ_MAX = 256;          // query rows per scan pass (two MMA M blocks of 128)
+constexpr int TILE_ROWS = 128;       // DB rows per TMA box / allocation granule
+constexpr int SCAN_TILE = 256;       // DB rows per scan tile (MMA N)
 constexpr int POOL_CAP = 128;        // candidate slots per (CTA, query) per pass
 constexpr int MAX_K = 128;
 constexpr int BRUTE_CHUNKS = 296;        // CTAs per query of the exact fallback scan (2 per SM)
@@ -30,6 +31,7 @@ struct nafp_index {
     float* x32 = nullptr;             // [cap][d] exact rows (re-rank, reconstruct, sequence scoring)
     __nv_bfloat16* x16 = nullptr;     // [cap][d] scan copy
     float* hn = nullptr;              // [cap] 0.5*|x|^2, +inf for unused rows
+    float* tile_hmin = nullptr;       // [cap / SCAN_TILE + 1] min of hn over each scan tile (prefilter offset)
     int32_t* maxn2 = nullptr;         // device scalar: bits of max |x|^2 (non-negative float)
     int64_t label_offset = 0;
     int64_t search_rows = -1;     // leading rows that take part in search (-1 = all); the rest are halo

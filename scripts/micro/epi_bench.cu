@@ -15,7 +15,7 @@ __global__ void k(int reps, long long* out, int* sink, float hval) {
     __shared__ __align__(16) float thr[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) { tmem_alloc(&tbase, 512); tmem_relinquish(); }
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) thr[i] = 1e30f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) thr[i] = (V == 7) ? -1e30f : 1e30f;
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const float h = hval + lane * 1e-9f;
@@ -65,6 +65,29 @@ __global__ void k(int reps, long long* out, int* sink, float hval) {
                 m0 = max(m0, (int)v[4*j4] - __float_as_int(t.x)); m1 = max(m1, (int)v[4*j4+1] - __float_as_int(t.y));
                 m2 = max(m2, (int)v[4*j4+2] - __float_as_int(t.z)); m3 = max(m3, (int)v[4*j4+3] - __float_as_int(t.w)); }
             p0 = max(max(m0, m1), max(m2, m3)) > 0;
+        } else if (V == 7) {   // packed FADD2 (v + (-thr)) and 3-input AND of the sign bits: fired <=> some sign bit clear
+            uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, a2 = 0xffffffffu, a3 = 0xffffffffu;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                uint64_t t01, t23;
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(t01), "=l"(t23) : "r"(ta + 16 * j4));
+                uint64_t v01, v23, d01, d23;
+                asm("mov.b64 %0, {%1,%2};" : "=l"(v01) : "r"(v[4*j4]), "r"(v[4*j4+1]));
+                asm("mov.b64 %0, {%1,%2};" : "=l"(v23) : "r"(v[4*j4+2]), "r"(v[4*j4+3]));
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(v01), "l"(t01));
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(v23), "l"(t23));
+                if (j4 & 1) { a2 &= (uint32_t)d01 & (uint32_t)(d01 >> 32); a3 &= (uint32_t)d23 & (uint32_t)(d23 >> 32); }
+                else        { a0 &= (uint32_t)d01 & (uint32_t)(d01 >> 32); a1 &= (uint32_t)d23 & (uint32_t)(d23 >> 32); }
+            }
+            p0 = (int)(a0 & a1 & a2 & a3) >= 0;
+        } else if (V == 8) {   // transposed scan: lane = query, one threshold register, 3-input max over the 32 columns
+            float m0 = -1e30f, m1 = -1e30f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                asm("max.f32 %0, %0, %1, %2;" : "+f"(m0) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j+1])));
+                asm("max.f32 %0, %0, %1, %2;" : "+f"(m1) : "f"(__uint_as_float(v[j+2])), "f"(__uint_as_float(v[j+3])));
+            }
+            p0 = fmaxf(m0, m1) > h;
         } else if (V == 6) {   // no compare at all: just load (lower bound)
             p0 = v[0] == 0x12345678u;
         }
@@ -102,5 +125,7 @@ int main() {
     run<3>("V3 FSETP only, thr in registers", out, sink);
     run<4>("V4 FADD+FMNMX max-reduce", out, sink);
     run<5>("V5 IADD+IMNMX max-reduce", out, sink);
+    run<7>("V7 FADD2 + LOP3 sign-AND", out, sink);
+    run<8>("V8 transposed: FMNMX3, thr per lane", out, sink);
     return 0;
 }
