@@ -63,21 +63,29 @@ __global__ void flat_fill_kernel(float* hn, int64_t from, int64_t to, float v) {
     if (i < to) hn[i] = v;
 }
 
-// one warp per scan tile: min of 0.5|x|^2 over the tile's stored rows (the scan's prefilter offset)
-__global__ void flat_tile_hmin_kernel(const float* __restrict__ hn, float* __restrict__ tile_hmin, int64_t tile_first,
+// one warp per scan tile: min and max of 0.5|x|^2 over the tile's stored rows.  min offsets the scan's
+// prefilter, max turns a tile's largest dot product into a lower bound of its largest score.
+__global__ void flat_tile_hmin_kernel(const float* __restrict__ hn, float2* __restrict__ tile_h, int64_t tile_first,
                                       int64_t n_tiles, int64_t n_rows) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_tiles) return;
     const int64_t t = tile_first + w;
-    float m = INFINITY;
+    float m = INFINITY, M = 0.f;
     for (int j = lane; j < SCAN_TILE; j += 32) {
         const int64_t r = t * SCAN_TILE + j;
-        if (r < n_rows) m = fminf(m, hn[r]);
+        if (r < n_rows) {
+            const float h = hn[r];
+            m = fminf(m, h);
+            M = fmaxf(M, h);
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) tile_hmin[t] = m;
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    }
+    if (lane == 0) tile_h[t] = make_float2(m, M);
 }
 
 // one warp per query row of the pass (rows >= nq are zero padding).  The pass takes rows
@@ -127,9 +135,9 @@ constexpr int SLOT_BYTES = SCAN_TILE * 128;                // 32 KB: one 64-colu
 constexpr int BOX_BYTES = TILE_ROWS * 128;                 // 16 KB per TMA box (128 rows)
 constexpr int Q_KB_BYTES = NQ_MAX * 128;                   // 32 KB: one K block of the query operand
 constexpr int Q_BYTES_MAX = 2 * Q_KB_BYTES;                // 64 KB
-constexpr int SCAN_SMEM = Q_BYTES_MAX + RING_SLOTS * SLOT_BYTES + 2 * NQ_MAX * 4 + 256 + 1024;
+constexpr int H_RING = 4;                               // tiles of 0.5|x|^2 kept in shared memory
+constexpr int SCAN_SMEM = Q_BYTES_MAX + RING_SLOTS * SLOT_BYTES + H_RING * SCAN_TILE * 4 + 2 * NQ_MAX * 4 + 256 + 1024;
 constexpr int NEG_INF_ORD = static_cast<int>(0x807FFFFFu);  // f2ord(-inf)
-constexpr int MAXONLY_CAP = 24;     // at most this many leading tiles are scanned max-only and re-scanned
 static_assert(PART_COLS == 64, "epilogue reads two 32-column chunks per unit");
 
 struct ScanBars {
@@ -140,8 +148,6 @@ struct ScanBars {
     uint64_t qfull;
     uint32_t tmem_base;
     int done;          // epilogue warps that finished
-    int decided;       // epilogue warps that fixed their number of max-only tiles
-    int redo[EPI_WARPS];   // ... and that number, per epilogue warp
 };
 
 __device__ __forceinline__ void smem_red_max(int* p, int v) {
@@ -169,23 +175,11 @@ __device__ __forceinline__ void mbar_arrive_lane0(uint64_t* bar, int lane) {
         "r"(lane)
         : "memory");
 }
-// all epilogue warps have fixed how many leading tiles they scanned max-only -> the maximum
-__device__ __forceinline__ int wait_redo_count(ScanBars* bars) {
-    uint32_t spins = 0;
-    while (smem_ld_volatile(&bars->decided) < EPI_WARPS) {
-        __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();
-    }
-    int r = 0;
-    for (int w = 0; w < EPI_WARPS; ++w) r = max(r, smem_ld_volatile(&bars->redo[w]));
-    return r;
-}
-
 // one survivor of the prefilter: exact bf16 score against the exact threshold, then the CTA's pool
-__device__ __noinline__ void scan_append(float v, float t_exact, uint32_t row, uint32_t n_search, const float* __restrict__ hn,
-                                         int* cnt_q, int* lmax_q, uint64_t* pool_q) {
+__device__ __forceinline__ void scan_append(float v, float h, float t_exact, uint32_t row, uint32_t n_search, int* cnt_q, int* lmax_q,
+                                         uint64_t* pool_q) {
     if (row >= n_search) return;                 // halo / padding rows never score
-    const float s = v - __ldg(hn + row);
+    const float s = v - h;
     if (s > t_exact) {
         const int so = f2ord(s);
         const int pos = smem_atom_inc(cnt_q);
@@ -201,14 +195,15 @@ __device__ __noinline__ void scan_append(float v, float t_exact, uint32_t row, u
 // tile's minimum (tile_hmin) and is applied exactly only to the few scores that pass it.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                 const float* __restrict__ hn, const float* __restrict__ tile_hmin, int64_t n_search, int n_tiles, int nq,
+                 const float* __restrict__ hn, const float2* __restrict__ tile_h, int64_t n_search, int n_tiles, int nq,
                  int n_half, int kg, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
                  int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_s = smem;                                   // [kb 2][256 query rows][128 B]
     uint8_t* b_s = smem + Q_BYTES_MAX;                     // [slot][256 DB rows][128 B]
-    int* lmax_s = reinterpret_cast<int*>(b_s + RING_SLOTS * SLOT_BYTES);
+    float* h_s = reinterpret_cast<float*>(b_s + RING_SLOTS * SLOT_BYTES);     // [H_RING][256] 0.5|x|^2 of the tile's rows
+    int* lmax_s = reinterpret_cast<int*>(h_s + H_RING * SCAN_TILE);
     int* cnt_s = lmax_s + NQ_MAX;
     ScanBars* bars = reinterpret_cast<ScanBars*>(cnt_s + NQ_MAX);
 
@@ -216,12 +211,10 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int G = gridDim.x;
     const int cta = blockIdx.x;
-    const int per = n_tiles / G, rem = n_tiles % G;
-    const int t0 = cta * per + min(cta, rem);
-    const int n_own = per + (cta < rem ? 1 : 0);
-    // Iterations 0..n_own-1 visit the CTA's tiles once.  Each epilogue warp scans the first R_w tiles
-    // "max-only" (no shared threshold exists yet, so it only feeds the running maxima); iterations
-    // n_own..n_own+R-1 (R = max R_w) re-visit those tiles with the threshold.
+    // tiles are dealt round-robin (tile = cta + i G): rows that many queries match -- the reference appends
+    // the real database after the dummy one -- are spread over all CTAs instead of loading the last few
+    const int n_own = (n_tiles - cta + G - 1) / G;
+    // Iterations 0..n_own-1 visit the CTA's tiles once, iteration n_own re-visits tile 0 (see the epilogue).
 
     for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
         lmax_s[i] = INT_MIN;
@@ -240,8 +233,6 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         mbar_init(&bars->qfull, 1);
         bars->done = 0;
-        bars->decided = 0;
-        for (int w = 0; w < EPI_WARPS; ++w) bars->redo[w] = 0;
         mbar_fence_init();
     }
     if (warp == MMA_WARP) {
@@ -261,21 +252,25 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int kb = 0; kb < 2; ++kb)
                 for (int r0 = 0; r0 < q_rows; r0 += 32)
                     tma_load_2d(q_s + kb * Q_KB_BYTES + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
-            int n_iter = n_own;
+            const int n_iter = n_own + 1;          // tile 0 is visited twice (max-only, then with thresholds)
             for (int i = 0; i < n_iter; ++i) {
-                const int tile = t0 + (i < n_own ? i : i - n_own);
+                const int tile = i < n_own ? cta + i * G : cta;
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const int kc = 2 * i + kb;
                     const int s = kc % RING_SLOTS;
                     const uint32_t ph = (kc / RING_SLOTS) & 1;
                     mbar_wait_parked(&bars->empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars->full[s], SLOT_BYTES);
+                    mbar_arrive_expect_tx(&bars->full[s], SLOT_BYTES + (kb == 0 ? SCAN_TILE * 4 : 0));
+                    // the tile's 0.5|x|^2 travel with its first K block.  Ring of 4: entry i is rewritten for
+                    // tile i+4, whose load is issued after tile i+2's MMAs, which start after tile i's epilogue
+                    if (kb == 0)
+                        bulk_load_1d(h_s + (i % H_RING) * SCAN_TILE, hn + static_cast<int64_t>(tile) * SCAN_TILE, SCAN_TILE * 4,
+                                     &bars->full[s]);
                     uint8_t* dst = b_s + s * SLOT_BYTES;
                     tma_load_2d(dst, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE);
                     tma_load_2d(dst + BOX_BYTES, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE + TILE_ROWS);
                 }
-                if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
             }
         }
         __syncwarp();
@@ -290,7 +285,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint64_t adesc0 = umma_desc_sw128(smem_u32(q_s));
         const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_s));
         mbar_wait_parked(&bars->qfull, 0);
-        int n_iter = n_own;
+        const int n_iter = n_own + 1;
         uint32_t uc = 0;
         for (int i = 0; i < n_iter; ++i) {
             const int s0 = (2 * i) % RING_SLOTS, s1 = s0 + 1;
@@ -324,7 +319,6 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 __syncwarp();
             }
-            if (i == n_own - 1) n_iter = n_own + wait_redo_count(bars);
         }
         __syncwarp();
     } else if (warp < EPI_WARPS) {
@@ -347,149 +341,158 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             t_pre[hq] = t_exact[hq];
         }
         uint64_t* my_pool = pool + static_cast<int64_t>(cta) * NQ_MAX * POOL_CAP;
-        bool normal = false;      // warp-uniform: thresholds of all of this warp's queries are known
-        bool all_valid = false;
-        int my_redo = 0;
-        int n_iter = n_own;
-        uint32_t uc = 0;
         const uint32_t ns32 = static_cast<uint32_t>(n_search);
-        float hmin_next = n_own > 0 ? __ldg(tile_hmin + t0) : 0.f;
-        for (int i = 0; i < n_iter; ++i) {
-            const bool second_visit = i >= n_own;
-            const int tile = t0 + (second_visit ? i - n_own : i);
-            const float hmin_t = hmin_next;
-            {
-                const int inext = i + 1;
-                const int tnext = t0 + (inext >= n_own ? inext - n_own : inext);
-                hmin_next = tnext < n_tiles ? __ldg(tile_hmin + tnext) : 0.f;
-            }
-            // shared thresholds of this thread's queries: loads issued now, consumed after the tile
-            const bool refresh = i < 12 || (i & 3) == 0 || i == n_own - 1;
-            int tg[2] = {INT_MIN, INT_MIN};
-            if (refresh) {
+        // shared thresholds of this thread's queries -> registers; true when all of the warp's are known
+        auto load_thresholds = [&](int (&tg)[2]) {
 #pragma unroll
-                for (int hq = 0; hq < 2; ++hq)
-                    if (active[hq]) tg[hq] = ld_relaxed(&Tg[hq * 128 + qd * 32 + lane]);
-            }
-            if (!normal && ((i >= 1 && all_valid) || i >= MAXONLY_CAP)) {
-                normal = true;
-                my_redo = i;
-                if (lane == 0) {
-                    bars->redo[e] = i;
-                    __threadfence_block();
-                    smem_atom_inc(&bars->decided);
+            for (int hq = 0; hq < 2; ++hq) tg[hq] = active[hq] ? ld_relaxed(&Tg[hq * 128 + qd * 32 + lane]) : INT_MIN;
+        };
+        auto apply_thresholds = [&](const int (&tg)[2], int i) -> bool {
+            bool valid = true;
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+                if (active[hq]) {
+                    if (tg[hq] > thr_ord[hq]) {
+                        if (dbg_first && part == 0 && thr_ord[hq] == NEG_INF_ORD)
+                            dbg_first[cta * NQ_MAX + hq * 128 + qd * 32 + lane] = i;
+                        thr_ord[hq] = tg[hq];
+                        const float t = ord2f(tg[hq]);
+                        t_exact[hq] = t;
+                        t_pre[hq] = t - fabsf(t) * (1.f / 1048576.f) - 1e-37f;
+                    }
+                    valid = valid && (thr_ord[hq] > NEG_INF_ORD);
                 }
-                __syncwarp();
             }
-            const bool maxonly = !normal;
-            const bool skip = second_visit && (i - n_own) >= my_redo;     // this warp already scanned it normally
+            return __all_sync(0xffffffffu, valid);
+        };
+        // publish this CTA's running maxima: warp e owns queries [QPW e, QPW e + QPW)
+        auto publish_maxima = [&]() {
+            const int q = e * QPW + lane;
+            if (lane < QPW && q < nq) {
+                const int m = smem_ld_volatile(&lmax_s[q]);
+                if (m > pub) {
+                    st_relaxed(&Mx[q * G + cta], m);
+                    pub = m;
+                }
+            }
+        };
+        // Tile 0 is scanned "max-only": it feeds the running maxima from which the shared thresholds
+        // are built.  The warp then waits (bounded) for the thresholds of its queries and scans
+        // everything else in normal mode; tile 0 is re-visited at the end (iteration n_own).
+        const int n_iter = n_own + 1;
+        uint32_t uc = 0;
+        float2 h_next = __ldg(tile_h + cta);
+        // developer probe (nq <= 248): ns since kernel start at which tile 0 / the threshold wait / the scan ended
+        const bool probe = dbg_first != nullptr && threadIdx.x == 0 && nq <= 248;
+        unsigned long long t_start = 0;
+        if (probe) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+        auto stamp = [&](int slot) {
+            if (probe) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                dbg_first[cta * NQ_MAX + 248 + slot] = static_cast<int>(t - t_start);
+            }
+        };
+        for (int i = 0; i < n_iter; ++i) {
+            if (i == 1) stamp(0);
+            if (i == 2) stamp(2);
+            if (i == n_own) stamp(3);
+            const bool maxonly = i == 0;
+            const int tile = i < n_own ? cta + i * G : cta;
+            const float2 h_t = h_next;     // {min, max} of 0.5|x|^2 over the tile
+            {
+                const int tnext = i + 1 < n_own ? tile + G : cta;
+                h_next = __ldg(tile_h + tnext);
+            }
+            int tg[2] = {INT_MIN, INT_MIN};
+            const bool rf = i > 1 && (i < 32 || (i & 3) == 0);      // loads issued now, consumed after the tile
+            if (i == 1) {
+                bool ok = false;
+                for (int spin = 0; spin < 4096 && !ok; ++spin) {
+                    publish_maxima();          // the other warps' tile-0 maxima of the queries this warp publishes
+                    load_thresholds(tg);
+                    ok = apply_thresholds(tg, i);
+                    if (!ok) __nanosleep(100);
+                }
+                // not ok after ~0.5 ms: scan on with -inf thresholds; the pools overflow and the exact
+                // fallback answers those queries
+                stamp(1);
+            } else if (rf) {
+                load_thresholds(tg);
+            }
             const uint32_t row0 = static_cast<uint32_t>(tile) * SCAN_TILE + part * PART_COLS;
             // prefilter: s = v - h > T  implies  v > T + min_tile(h) (minus a rounding margin)
-            const float hm = hmin_t * (1.f - 1.f / 1048576.f);
-            float hA = 0.f, hB = 0.f;
-            if (maxonly && !skip) {
-                const uint32_t ra = row0 + lane, rb = row0 + 32 + lane;
-                hA = ra < ns32 ? __ldg(hn + ra) : INFINITY;
-                hB = rb < ns32 ? __ldg(hn + rb) : INFINITY;
-            }
+            const float hm = h_t.x * (1.f - 1.f / 1048576.f);
+            // max-only: max_j v_j - max_tile(h) is a lower bound of the tile's best score, good enough for
+            // the running maxima; only a tile with halo / padding rows needs the exact per-row form
+            const bool whole = static_cast<uint32_t>(tile + 1) * SCAN_TILE <= ns32;
+            const float hM = h_t.y * (1.f + 1.f / 1048576.f);
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
                 const uint32_t aph = (uc >> 1) & 1;
                 const int q = hq * 128 + qd * 32 + lane;
+                const bool act = hq == 0 ? active[0] : active[1];
+                const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
                 mbar_wait(&bars->tfull[acc], aph);
                 tc_fence_after();
-                if (!skip) {
-                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * SCAN_TILE + part * PART_COLS;
-                    uint32_t v0[32], v1[32];
-                    tmem_ld_32x32(taddr, v0);
-                    tmem_ld_32x32(taddr + 32, v1);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * SCAN_TILE + part * PART_COLS;
+                float munit = NEG_INF;
+#pragma unroll 1
+                for (int c = 0; c < PART_COLS / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c * 32, v);
                     tc_wait_ld();
+                    const float* hc = h_s + (i % H_RING) * SCAN_TILE + part * PART_COLS + c * 32;    // h of this chunk's rows
+                    if (maxonly && !whole) {
+                        const uint32_t r = row0 + c * 32 + lane;
+                        const float h = r < ns32 ? hc[lane] : INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) munit = fmaxf(munit, __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, h, j));
+                        continue;
+                    }
+                    // maxima of the four 8-column groups (FMNMX3), then of the chunk
+                    float gm[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float m = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                        m = fmax3(m, __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
+                        m = fmax3(m, __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
+                        gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+                    }
+                    const float ma = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
                     if (maxonly) {
-                        float m = NEG_INF;
+                        munit = fmaxf(munit, ma - hM);
+                        continue;
+                    }
+                    const bool fired = ma > tp;
+                    if (__any_sync(0xffffffffu, fired)) {
+                        // rare: this lane's query has a score above the prefilter among the 32 columns;
+                        // only the 8-column groups whose maximum fired are looked at
+                        if (fired) {
+                            const float te = hq == 0 ? t_exact[0] : t_exact[1];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            m = fmaxf(m, __uint_as_float(v0[j]) - __shfl_sync(0xffffffffu, hA, j));
-                            m = fmaxf(m, __uint_as_float(v1[j]) - __shfl_sync(0xffffffffu, hB, j));
-                        }
-                        if (hq == 0 ? active[0] : active[1]) smem_red_max(&lmax_s[q], f2ord(m));
-                    } else {
-                        float ma = __uint_as_float(v0[0]), mb = __uint_as_float(v1[0]);
+                            for (int g = 0; g < 4; ++g) {
+                                if (gm[g] > tp) {
 #pragma unroll
-                        for (int j = 1; j < 31; j += 2) {
-                            ma = fmax3(ma, __uint_as_float(v0[j]), __uint_as_float(v0[j + 1]));
-                            mb = fmax3(mb, __uint_as_float(v1[j]), __uint_as_float(v1[j + 1]));
-                        }
-                        ma = fmax3(ma, mb, __uint_as_float(v0[31]));
-                        ma = fmaxf(ma, __uint_as_float(v1[31]));
-                        const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
-                        const bool fired = ma > tp;
-                        if (__any_sync(0xffffffffu, fired)) {
-                            // rare: this lane's query has a score above the prefilter among the 64 columns
-                            if (fired) {
-                                const float te = hq == 0 ? t_exact[0] : t_exact[1];
-                                int* cq = &cnt_s[q];
-                                int* lq = &lmax_s[q];
-                                uint64_t* pq = my_pool + q * POOL_CAP;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (__uint_as_float(v0[j]) > tp) scan_append(__uint_as_float(v0[j]), te, row0 + j, ns32, hn, cq, lq, pq);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (__uint_as_float(v1[j]) > tp)
-                                        scan_append(__uint_as_float(v1[j]), te, row0 + 32 + j, ns32, hn, cq, lq, pq);
+                                    for (int j = 8 * g; j < 8 * g + 8; ++j)
+                                        if (__uint_as_float(v[j]) > tp)
+                                            scan_append(__uint_as_float(v[j]), hc[j], te, row0 + c * 32 + j, ns32, &cnt_s[q], &lmax_s[q],
+                                                        my_pool + q * POOL_CAP);
+                                }
                             }
-                            __syncwarp();
                         }
+                        __syncwarp();
                     }
                 }
+                if (maxonly && act) smem_red_max(&lmax_s[q], f2ord(munit));
                 tc_fence_before();
                 __syncwarp();
                 mbar_arrive_lane0(&bars->tempty[acc], lane);
             }
-            if (refresh) {
-                // publish this CTA's running maxima: warp e owns queries [QPW e, QPW e + QPW)
-                {
-                    const int q = e * QPW + lane;
-                    if (lane < QPW && q < nq) {
-                        const int m = smem_ld_volatile(&lmax_s[q]);
-                        if (m > pub) {
-                            st_relaxed(&Mx[q * G + cta], m);
-                            pub = m;
-                        }
-                    }
-                }
-                // consume the threshold loads issued at the top of the iteration
-                bool valid = true;
-#pragma unroll
-                for (int hq = 0; hq < 2; ++hq) {
-                    if (active[hq]) {
-                        if (tg[hq] > thr_ord[hq]) {
-                            if (dbg_first && part == 0 && thr_ord[hq] == NEG_INF_ORD)
-                                dbg_first[cta * NQ_MAX + hq * 128 + qd * 32 + lane] = i;
-                            thr_ord[hq] = tg[hq];
-                            const float t = ord2f(tg[hq]);
-                            t_exact[hq] = t;
-                            t_pre[hq] = t - fabsf(t) * (1.f / 1048576.f) - 1e-37f;
-                        }
-                        valid = valid && (thr_ord[hq] > NEG_INF_ORD);
-                    }
-                }
-                all_valid = __all_sync(0xffffffffu, valid);
-            }
-            if (i == n_own - 1) {
-                if (!normal) {       // thresholds never arrived: everything is re-scanned (tiny databases)
-                    normal = true;
-                    my_redo = n_own;
-                    if (lane == 0) {
-                        bars->redo[e] = n_own;
-                        __threadfence_block();
-                        smem_atom_inc(&bars->decided);
-                    }
-                    __syncwarp();
-                }
-                n_iter = n_own + wait_redo_count(bars);
-            }
+            if (rf) apply_thresholds(tg, i);
+            if (i < 32 || (i & 3) == 0 || i >= n_own - 1) publish_maxima();
         }
+        stamp(4);
         __syncwarp();
         // all epilogue warps are done appending before counts are published
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
@@ -812,11 +815,11 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     float* x32 = nullptr;
     __nv_bfloat16* x16 = nullptr;
     float* hn = nullptr;
-    float* tile_hmin = nullptr;
-    NAFP_CUDA(cudaMalloc(&tile_hmin, static_cast<size_t>(new_cap / SCAN_TILE + 2) * sizeof(float)));
+    float2* tile_hmin = nullptr;
+    NAFP_CUDA(cudaMalloc(&tile_hmin, static_cast<size_t>(new_cap / SCAN_TILE + 2) * sizeof(float2)));
     NAFP_CUDA(cudaMalloc(&x32, static_cast<size_t>(new_cap) * idx->d * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&x16, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16)));
-    NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap) * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap + SCAN_TILE) * sizeof(float)));
     NAFP_CUDA(cudaMemsetAsync(x16, 0, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16), ctx->stream));
     if (idx->n > 0) {
         NAFP_CUDA(cudaMemcpyAsync(x32, idx->x32, static_cast<size_t>(idx->n) * idx->d * sizeof(float),
@@ -825,14 +828,14 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
                                   cudaMemcpyDeviceToDevice, ctx->stream));
         NAFP_CUDA(cudaMemcpyAsync(hn, idx->hn, static_cast<size_t>(idx->n) * sizeof(float),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
-        NAFP_CUDA(cudaMemcpyAsync(tile_hmin, idx->tile_hmin, static_cast<size_t>((idx->n + SCAN_TILE - 1) / SCAN_TILE) * sizeof(float),
+        NAFP_CUDA(cudaMemcpyAsync(tile_hmin, idx->tile_hmin, static_cast<size_t>((idx->n + SCAN_TILE - 1) / SCAN_TILE) * sizeof(float2),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     }
     {
-        const int64_t cnt = new_cap - idx->n;
+        const int64_t cnt = new_cap + SCAN_TILE - idx->n;
         const int threads = 256;
         const int64_t blocks = (cnt + threads - 1) / threads;
-        flat_fill_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(hn, idx->n, new_cap, INFINITY);
+        flat_fill_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(hn, idx->n, new_cap + SCAN_TILE, INFINITY);
         ctx->launches++;
         NAFP_CUDA(cudaGetLastError());
     }

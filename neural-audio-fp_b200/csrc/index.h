@@ -16,7 +16,7 @@ constexpr int POOL_CAP = 128;        // candidate slots per (CTA, query) per pas
 constexpr int MAX_K = 128;
 constexpr int BRUTE_CHUNKS = 296;        // CTAs per query of the exact fallback scan (2 per SM)
 constexpr int BRUTE_SLOTS = 32;          // queries per fallback launch
-constexpr int SELECT_CAP = 2048;     // candidates re-ranked in fp32 per query, at most
+constexpr int SELECT_CAP = 4096;     // candidates re-ranked in fp32 per query, at most
 
 struct IvfPq;                        // ivfpq.cu
 
@@ -30,8 +30,8 @@ struct nafp_index {
     int64_t cap = 0;          // rows allocated (multiple of TILE_ROWS)
     float* x32 = nullptr;             // [cap][d] exact rows (re-rank, reconstruct, sequence scoring)
     __nv_bfloat16* x16 = nullptr;     // [cap][d] scan copy
-    float* hn = nullptr;              // [cap] 0.5*|x|^2, +inf for unused rows
-    float* tile_hmin = nullptr;       // [cap / SCAN_TILE + 1] min of hn over each scan tile (prefilter offset)
+    float* hn = nullptr;              // [cap + SCAN_TILE] 0.5*|x|^2, +inf for unused rows
+    float2* tile_hmin = nullptr;      // [cap / SCAN_TILE + 2] {min, max} of hn over each scan tile
     int32_t* maxn2 = nullptr;         // device scalar: bits of max |x|^2 (non-negative float)
     int64_t label_offset = 0;
     int64_t search_rows = -1;     // leading rows that take part in search (-1 = all); the rest are halo
