@@ -57,6 +57,40 @@ def test_flat_search_unnormalised_rows():
     assert_topk_matches(Dg, Ig, Do, Io, x, q, dtol=2e-3)
 
 
+def test_flat_search_zero_rows_and_ragged_adds():
+    """The scan's prefilter uses each 256-row tile's min 0.5|x|^2: all-zero rows (silence), mixed norms
+    inside a tile and add() calls that straddle tile boundaries / grow the allocation must not change
+    the answer."""
+    rng = np.random.default_rng(15)
+    x = rng.standard_normal((70001, 128)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    x[::977] = 0.0                                   # silent segments
+    x[5000:5300] *= rng.uniform(0.3, 2.0, (300, 1)).astype(np.float32)
+    q = x[rng.integers(0, len(x), 140)] + 0.05 * rng.standard_normal((140, 128)).astype(np.float32)
+    cuts = [0, 100, 1133, 1134, 20000, 20255, 45001, 70001]
+    g = _gpu_index([x[a:b] for a, b in zip(cuts[:-1], cuts[1:])])      # no reserve(): grows by doubling
+    o = _oracle_index([x])
+    for nq in (140, 129, 128, 1):                    # two query halves (second mostly padding), one half, one row
+        Dg, Ig = g.search(q[:nq], 20)
+        Do, Io = o.search(q[:nq], 20)
+        assert_topk_matches(Dg, Ig, Do, Io, x, q[:nq], dtol=2e-3)
+
+
+def test_flat_search_rows_limit_excludes_halo():
+    """set_search_rows(m): rows >= m are stored (sequence scoring reads them) but never returned."""
+    from nafp_b200 import synth
+    dummy, db, query = synth.synth_search_set(30000, 590, seed=4)
+    x = np.concatenate([dummy, db])
+    g = _gpu_index([x])
+    m = 30000 + 300 + 7                              # inside a tile
+    g.set_search_rows(m)
+    o = _oracle_index([x[:m]])
+    Dg, Ig = g.search(query[:50], 20)
+    Do, Io = o.search(query[:50], 20)
+    assert Ig.max() < m
+    assert_topk_matches(Dg, Ig, Do, Io, x[:m], query[:50])
+
+
 def test_flat_search_fewer_rows_than_k():
     rng = np.random.default_rng(6)
     x = rng.standard_normal((7, 128)).astype(np.float32)
