@@ -389,6 +389,36 @@ def run_gpu(args):
                 "top1_hit_rate": [float(100.0 * np.mean(mp[:, si, 0] == test_ids + 1_000_000)) for si in range(len(SEQ_LENS))]}
         del midx
 
+    # ---- IVF-PQ at the mini scale: same job through the approximate index the reference
+    # builds for index_type "ivfpq" (nlist 256, M 64, 8 bit, nprobe 40), host API incl. H2D / D2H
+    ivf = None
+    if world == 1 and not args.no_mini and not args.no_ivfpq and n_dummy >= 1_000_000:
+        from nafp_b200.eval.utils.get_index import IVFPQ, Index
+        t_ivf = time.time()
+        iidx = Index(IVFPQ, 128, nlist=256, pq_m=64, pq_nbits=8, device=local_rank)
+        buf = torch.empty((1_000_000, 128), dtype=torch.float32, device=dev)
+        check(lib.nafp_synth_fp_rows(ctx.h, 11, 0, 1_000_000, 59, 0.5, ctypes.c_void_p(buf.data_ptr())))
+        iidx.train(buf[:: 10].contiguous().cpu().numpy())          # 100,000 training rows (<= 256 per centroid is what faiss samples)
+        t_train = time.time() - t_ivf
+        iidx.reserve(1_000_000 + N_DB)
+        iidx.add_dev(buf.data_ptr(), 1_000_000)
+        iidx.add_dev(dbt.data_ptr(), N_DB)
+        iidx.nprobe = 40
+        torch.cuda.synchronize(dev)
+        del buf
+        sl_host = np.asarray(SEQ_LENS, np.int32)
+
+        def ivf_step():
+            result["ivf"] = iidx.seq_match(query_host, test_ids, sl_host, K_PROBE)
+
+        ms_ivf = time_steps(torch, dev, ivf_step, args.steps, args.warmup, barrier)
+        ip = result["ivf"][0]
+        ivf = {"index": "IVFPQ nlist 256, M 64, 8 bit, nprobe 40", "db_rows": 1_000_000 + N_DB,
+               "value": n_queries / (ms_ivf * 1e-3), "unit": "queries/s", "ms_per_step": ms_ivf, "train_s": t_train,
+               "through": "host API (nafp_seq_match: H2D queries, D2H predictions inside the timed region)",
+               "top1_hit_rate": [float(100.0 * np.mean(ip[:, si, 0] == test_ids + 1_000_000)) for si in range(len(SEQ_LENS))]}
+        del iidx
+
     # ---- CPU baseline (rank 0, N = 1): the oracle port on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -414,7 +444,7 @@ def run_gpu(args):
                 "roofline": roofline, "cpu_baseline": cpu,
                 "top1_hit_rate": dict(zip(map(str, SEQ_LENS), top1)),
                 "search_stats_per_step": {k: v / args.steps for k, v in stats.items()},
-                "fingerprint": fp, "mini_1M": mini, "db_build_s": t_build}
+                "fingerprint": fp, "mini_1M": mini, "ivfpq_1M": ivf, "db_build_s": t_build}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -430,6 +460,7 @@ def main():
     ap.add_argument("--db-rows", type=int, default=N_DUMMY_FULL, help="dummy_db rows (full scale: 56,000,000)")
     ap.add_argument("--no-fp", action="store_true")
     ap.add_argument("--no-mini", action="store_true")
+    ap.add_argument("--no-ivfpq", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

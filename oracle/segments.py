@@ -12,6 +12,8 @@ Restates the no-augmentation path the reference's generator takes for fingerprin
   cast to float32 and shaped (n, 1, T).
 
 Uses only the standard-library ``wave`` module, like the reference.
+PINNED: bit-identical to the reference's ``get_fns_seg_list`` + ``load_audio`` outputs on six WAV files
+of awkward lengths (``tests/golden/ref_segments.npz``, ``tests/test_reference_golden.py``).
 """
 from __future__ import annotations
 

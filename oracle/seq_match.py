@@ -12,6 +12,8 @@ index object exposing ``search(q, k) -> (D, I)``:
 * ``:236-243``  top1_exact / top1_near / top3 / top10 against gt = test_id + n_dummy (``:189``)
 
 ``recon`` is the reference's ``fake_recon_index`` (``:167-171``) = [dummy_db; db] rows.
+PINNED: reproduces ``raw_score.npy`` written by the reference's own loop on a 61,180-row fixture
+(``tests/golden/ref_eval_flat.npz``, ``tests/test_reference_golden.py``).
 The only deviation: ``argsort`` is made stable so that ties resolve to the lower candidate id
 (the reference's quicksort order on exact ties is unspecified).
 """

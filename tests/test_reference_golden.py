@@ -1,0 +1,71 @@
+"""Golden vectors produced by the reference's OWN code (tests/golden/make_reference_golden.py ran
+``model/utils/audio_utils.py`` and the unmodified evaluation loop of ``eval/eval_faiss.py`` in the build
+container): the oracle restatements and the product must reproduce them exactly.  These are the parts
+of the hot path that pin the oracle to the reference itself."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(HERE, "golden", "make_reference_golden.py"))
+gold = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gold)          # helpers only; nothing under /root/reference is touched at import time
+
+
+@pytest.fixture(scope="module")
+def ref_segments():
+    return np.load(os.path.join(HERE, "golden", "ref_segments.npz"))
+
+
+@pytest.fixture(scope="module")
+def ref_eval():
+    return np.load(os.path.join(HERE, "golden", "ref_eval_flat.npz"))
+
+
+def test_segmenter_oracle_and_product_match_reference_loader(tmp_path, ref_segments):
+    from nafp_b200.model import dataset
+    from oracle import segments as oseg
+    paths = gold.segment_wavs(str(tmp_path))
+    want = ref_segments["audio"]                                   # (n_segments, 8000) float32 from load_audio
+    # segment enumeration (get_fns_seg_list, segment_mode='all')
+    sl = oseg.seg_list(paths)
+    assert [paths.index(f) for f, _ in sl] == ref_segments["file_index"].tolist()
+    assert [s for _, s in sl] == ref_segments["seg_index"].tolist()
+    # oracle loader and the product's single-read segmenter, batch size 7 (ragged last batch)
+    got_o = np.concatenate([b[:, 0, :] for b in oseg.batches(paths, bsz=7)])
+    np.testing.assert_array_equal(got_o, want)
+    seq = dataset.SegmentSequence(paths, bsz=7)
+    assert seq.n_samples == len(want)
+    got_p = np.concatenate([seq[i][0][:, 0, :] for i in range(len(seq))])
+    np.testing.assert_array_equal(got_p, want)
+
+
+def test_oracle_matcher_reproduces_reference_eval_loop(ref_eval):
+    """raw_score.npy written by the reference's loop (with an exact numpy stand-in for faiss.IndexFlatL2)."""
+    from oracle import seq_match
+    from oracle.flat_index import FlatL2
+    dummy, db, query = gold.eval_set()
+    ids = ref_eval["test_ids"]
+    np.testing.assert_array_equal(ids, np.asarray(gold.EVAL["test_ids"]))
+    idx = FlatL2(128)
+    idx.add(dummy)
+    idx.add(db)
+    lens = list(map(int, gold.EVAL["seq_lens"].split()))
+    raw, _ = seq_match.evaluate(idx, query, np.concatenate([dummy, db]), len(dummy), ids, lens, gold.EVAL["k_probe"])
+    np.testing.assert_array_equal(raw, ref_eval["raw_score"])
+    assert 20.0 < 100 * ref_eval["raw_score"][:, 0].mean() < 40.0          # a discriminating fixture: misses exist
+
+
+@pytest.mark.gpu
+def test_product_cli_reproduces_reference_eval_loop(tmp_path, ref_eval):
+    """The product's evaluate entry point on the same emb_dir writes the same raw_score.npy / test_ids.npy."""
+    from nafp_b200.eval.eval_search import run_eval
+    emb = str(tmp_path) + "/"
+    gold.write_emb_dir(emb)
+    ids_path = os.path.join(emb, "ids.npy")
+    np.save(ids_path, np.asarray(gold.EVAL["test_ids"], np.int64))
+    run_eval(emb, None, 'l2', False, 1e7, ids_path, gold.EVAL["seq_lens"], gold.EVAL["k_probe"], 5)
+    np.testing.assert_array_equal(np.load(emb + "raw_score.npy"), ref_eval["raw_score"])
+    np.testing.assert_array_equal(np.load(emb + "test_ids.npy"), ref_eval["test_ids"])
