@@ -127,7 +127,7 @@ __global__ void flat_prep_kernel(const float* __restrict__ q_all, const int32_t*
 constexpr int RING_SLOTS = 4;                           // K-block slots of the DB ring
 constexpr int EPI_WARPS = 16;
 constexpr int SCAN_THREADS = (3 + EPI_WARPS) * 32;   // warps 0..15 epilogue, 16 reducer, 17 TMA, 18 MMA (+TMEM alloc)
-constexpr int REDUCER_WARP = EPI_WARPS, TMA_WARP = EPI_WARPS + 1, MMA_WARP = EPI_WARPS + 2;   // the SM's warp arbiter
+constexpr int TMA_WARP = EPI_WARPS + 1, MMA_WARP = EPI_WARPS + 2;   // (warp EPI_WARPS is the reducer.)  The SM's warp arbiter
                                                      // favours high warp ids: the MMA issuer must never wait for a slot
 constexpr int EPI_PARTS = EPI_WARPS / 4;          // the 4 warps of a TMEM lane quadrant split the tile's 256 DB rows
 constexpr int PART_COLS = SCAN_TILE / EPI_PARTS;  // 64 DB rows (accumulator columns) per warp per unit
@@ -574,8 +574,14 @@ __device__ void bitonic_sort_desc(uint64_t* keys, int n) {
     }
 }
 
+struct SelBatch {
+    int np[SEL_SLOTS];       // query rows of the pass held in every slot
+    int grid_alloc;          // CTA dimension the pool / cnt arrays were allocated with
+};
+
+// grid (NQ_MAX, slots): block (q, slot) answers row q of the scan pass parked in `slot`
 __global__ void __launch_bounds__(256)
-flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __restrict__ q32,
+flat_select_kernel(SelBatch batch, int k, int grid_scan, int64_t n_rows, const float* __restrict__ q32,
                    const float* __restrict__ qn2, const float* __restrict__ x32, const float* __restrict__ hn,
                    const int32_t* __restrict__ maxn2, const int32_t* __restrict__ Tg,
                    const uint64_t* __restrict__ pool, const int32_t* __restrict__ cnt, int32_t* __restrict__ flags,
@@ -587,6 +593,15 @@ flat_select_kernel(int nq, int k, int grid_scan, int64_t n_rows, const float* __
     __shared__ uint64_t keys[SELECT_CAP];
     __shared__ int total_s;
     const int q = blockIdx.x;
+    const int slot = blockIdx.y;
+    if (q >= batch.np[slot]) return;
+    q32 += static_cast<int64_t>(slot) * NQ_MAX * D128;
+    qn2 += slot * NQ_MAX;
+    Tg += slot * NQ_MAX;
+    pool += static_cast<int64_t>(slot) * batch.grid_alloc * NQ_MAX * POOL_CAP;
+    cnt += static_cast<int64_t>(slot) * batch.grid_alloc * NQ_MAX;
+    flags += slot * NQ_MAX;
+    gidx += slot * NQ_MAX;
     const int64_t g = gidx[q];
     if (flags[q] != 0) {                 // pool overflow seen by the scan
         if (threadIdx.x == 0) {
@@ -894,14 +909,14 @@ static int ensure_scratch(nafp_index* idx) {
     NAFP_REQUIRE(idx->grid <= 160, NAFP_ERR_UNSUPPORTED, "flat scan: %d SMs (reducer handles <= 160)", idx->grid);
     const int G = idx->grid;
     NAFP_CUDA(cudaMalloc(&idx->qbf, NQ_MAX * D128 * sizeof(__nv_bfloat16)));
-    NAFP_CUDA(cudaMalloc(&idx->q32, NQ_MAX * D128 * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&idx->qn2, NQ_MAX * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&idx->q32, SEL_SLOTS * NQ_MAX * D128 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&idx->qn2, SEL_SLOTS * NQ_MAX * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&idx->Mx, static_cast<size_t>(NQ_MAX) * G * sizeof(int32_t)));
-    NAFP_CUDA(cudaMalloc(&idx->Tg, NQ_MAX * sizeof(int32_t)));
-    NAFP_CUDA(cudaMalloc(&idx->pool, static_cast<size_t>(G) * NQ_MAX * POOL_CAP * sizeof(uint64_t)));
-    NAFP_CUDA(cudaMalloc(&idx->cnt, static_cast<size_t>(G) * NQ_MAX * sizeof(int32_t)));
-    NAFP_CUDA(cudaMalloc(&idx->flags, NQ_MAX * sizeof(int32_t)));
-    NAFP_CUDA(cudaMalloc(&idx->gidx, NQ_MAX * sizeof(int64_t)));
+    NAFP_CUDA(cudaMalloc(&idx->Tg, SEL_SLOTS * NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->pool, SEL_SLOTS * static_cast<size_t>(G) * NQ_MAX * POOL_CAP * sizeof(uint64_t)));
+    NAFP_CUDA(cudaMalloc(&idx->cnt, SEL_SLOTS * static_cast<size_t>(G) * NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->flags, SEL_SLOTS * NQ_MAX * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&idx->gidx, SEL_SLOTS * NQ_MAX * sizeof(int64_t)));
     NAFP_CUDA(cudaMalloc(&idx->brute_part, static_cast<size_t>(BRUTE_SLOTS) * BRUTE_CHUNKS * MAX_K * sizeof(uint64_t)));
     NAFP_CUDA(cudaMalloc(&idx->stats, 8 * sizeof(unsigned long long)));
     NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -930,28 +945,44 @@ static int brute_rounds(nafp_index* idx, const float* q_dev, const int32_t* list
     return NAFP_OK;
 }
 
-static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_list, int src_off, int64_t p0, int np, int k,
-                     int kg, int grid_scan, int n_tiles, int64_t n_search, int32_t* fail_list, int32_t* fail_count,
-                     float* D_dev, int64_t* I_dev) {
+static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_list, int src_off, int64_t p0, int np, int kg,
+                     int grid_scan, int n_tiles, int64_t n_search, int slot) {
     nafp_ctx* ctx = idx->ctx;
     const int n_half = np > 128 ? 2 : 1;
     const int nq_pad = n_half * 128;
+    const int64_t G = idx->grid;
+    float* q32 = idx->q32 + static_cast<int64_t>(slot) * NQ_MAX * D128;
+    float* qn2 = idx->qn2 + slot * NQ_MAX;
+    int32_t* Tg = idx->Tg + slot * NQ_MAX;
+    uint64_t* pool = idx->pool + static_cast<int64_t>(slot) * G * NQ_MAX * POOL_CAP;
+    int32_t* cnt = idx->cnt + static_cast<int64_t>(slot) * G * NQ_MAX;
+    int32_t* flags = idx->flags + slot * NQ_MAX;
+    int64_t* gidx = idx->gidx + slot * NQ_MAX;
     flat_prep_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, ctx->stream>>>(q_dev, src_list, src_off, p0, np, nq_pad, grid_scan,
-                                                                         idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
-                                                                         idx->flags, idx->gidx);
+                                                                         idx->qbf, q32, qn2, idx->Mx, Tg, flags, gidx);
     const bool prof = idx->profile && idx->prof_n < PROF_RING;
     if (prof) cudaEventRecord(idx->prof_ev[2 * idx->prof_n], ctx->stream);
     flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, idx->tile_hmin, n_search,
-                                                                          n_tiles, np, n_half, kg, idx->Mx, idx->Tg, idx->pool, idx->cnt,
-                                                                          idx->flags, idx->dbg_first);
+                                                                          n_tiles, np, n_half, kg, idx->Mx, Tg, pool, cnt, flags,
+                                                                          idx->dbg_first);
     if (prof) {
         cudaEventRecord(idx->prof_ev[2 * idx->prof_n + 1], ctx->stream);
         idx->prof_n++;
     }
-    flat_select_kernel<<<np, 256, 0, ctx->stream>>>(np, k, grid_scan, n_search, idx->q32, idx->qn2, idx->x32, idx->hn,
-                                                    idx->maxn2, idx->Tg, idx->pool, idx->cnt, idx->flags, idx->gidx,
-                                                    fail_list, fail_count, idx->label_offset, D_dev, I_dev, idx->stats);
-    ctx->launches += 3;
+    ctx->launches += 2;
+    idx->last_slot = slot;
+    return NAFP_OK;
+}
+
+// exact re-rank + proof of every pass parked in slots [0, n_slots): one launch
+static int select_batch(nafp_index* idx, const SelBatch& batch, int n_slots, int k, int grid_scan, int64_t n_search,
+                        int32_t* fail_list, int32_t* fail_count, float* D_dev, int64_t* I_dev) {
+    nafp_ctx* ctx = idx->ctx;
+    flat_select_kernel<<<dim3(NQ_MAX, n_slots), 256, 0, ctx->stream>>>(batch, k, grid_scan, n_search, idx->q32, idx->qn2, idx->x32,
+                                                                       idx->hn, idx->maxn2, idx->Tg, idx->pool, idx->cnt, idx->flags,
+                                                                       idx->gidx, fail_list, fail_count, idx->label_offset, D_dev,
+                                                                       I_dev, idx->stats);
+    ctx->launches++;
     return NAFP_OK;
 }
 
@@ -986,10 +1017,18 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
     int32_t* list2 = idx->fail_list + nq;            // rows that failed the retry pass too
     int32_t* counts = idx->fail_list + 2 * nq;       // [2]
     NAFP_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), ctx->stream));
+    SelBatch batch;
+    batch.grid_alloc = idx->grid;
+    int slot = 0;
     for (int64_t p0 = 0; p0 < nq; p0 += NQ_MAX) {
         const int np = static_cast<int>(nq - p0 < NQ_MAX ? nq - p0 : NQ_MAX);
-        NAFP_TRY(scan_pass(idx, q_dev, nullptr, 0, p0, np, k, kg, grid_scan, n_tiles, n_search, list1, counts, D_dev, I_dev));
+        NAFP_TRY(scan_pass(idx, q_dev, nullptr, 0, p0, np, kg, grid_scan, n_tiles, n_search, slot));
+        batch.np[slot++] = np;
         idx->host_passes++;
+        if (slot == SEL_SLOTS || p0 + NQ_MAX >= nq) {
+            NAFP_TRY(select_batch(idx, batch, slot, k, grid_scan, n_search, list1, counts, D_dev, I_dev));
+            slot = 0;
+        }
     }
     NAFP_CUDA(cudaGetLastError());
     int32_t h[2] = {0, 0};
@@ -998,11 +1037,16 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
     if (h[0] > 0) {
         // second chance: a threshold about one spread of the per-CTA maxima lower (~2x the survivors)
         const int kg_retry = 2 * kg < grid_scan - 2 ? 2 * kg : (grid_scan - 2 > kg ? grid_scan - 2 : kg);
+        slot = 0;
         for (int off = 0; off < h[0]; off += NQ_MAX) {
             const int np = h[0] - off < NQ_MAX ? h[0] - off : NQ_MAX;
-            NAFP_TRY(scan_pass(idx, q_dev, list1, off, 0, np, k, kg_retry, grid_scan, n_tiles, n_search, list2, counts + 1,
-                               D_dev, I_dev));
+            NAFP_TRY(scan_pass(idx, q_dev, list1, off, 0, np, kg_retry, grid_scan, n_tiles, n_search, slot));
+            batch.np[slot++] = np;
             idx->host_passes++;
+            if (slot == SEL_SLOTS || off + NQ_MAX >= h[0]) {
+                NAFP_TRY(select_batch(idx, batch, slot, k, grid_scan, n_search, list2, counts + 1, D_dev, I_dev));
+                slot = 0;
+            }
         }
         NAFP_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1173,7 +1217,7 @@ int nafp_index_debug_enable(nafp_index* idx, int32_t* cnt_out, int32_t* first_ou
         NAFP_CUDA(cudaMemset(idx->dbg_first, 0xFF, n * 4));
     }
     if (grid_out) *grid_out = idx->grid;
-    if (cnt_out) NAFP_CUDA(cudaMemcpy(cnt_out, idx->cnt, n * 4, cudaMemcpyDeviceToHost));
+    if (cnt_out) NAFP_CUDA(cudaMemcpy(cnt_out, idx->cnt + static_cast<size_t>(idx->last_slot) * n, n * 4, cudaMemcpyDeviceToHost));
     if (first_out) {
         NAFP_CUDA(cudaMemcpy(first_out, idx->dbg_first, n * 4, cudaMemcpyDeviceToHost));
         NAFP_CUDA(cudaMemset(idx->dbg_first, 0xFF, n * 4));
@@ -1186,9 +1230,9 @@ int nafp_index_debug_last_pass(nafp_index* idx, int32_t* flags256, float* thr256
     nafp_ctx* ctx = idx->ctx;
     NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     std::vector<int32_t> tg(NQ_MAX), cnt(static_cast<size_t>(idx->grid) * NQ_MAX);
-    NAFP_CUDA(cudaMemcpy(flags256, idx->flags, NQ_MAX * 4, cudaMemcpyDeviceToHost));
-    NAFP_CUDA(cudaMemcpy(tg.data(), idx->Tg, NQ_MAX * 4, cudaMemcpyDeviceToHost));
-    NAFP_CUDA(cudaMemcpy(cnt.data(), idx->cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+    NAFP_CUDA(cudaMemcpy(flags256, idx->flags + idx->last_slot * NQ_MAX, NQ_MAX * 4, cudaMemcpyDeviceToHost));
+    NAFP_CUDA(cudaMemcpy(tg.data(), idx->Tg + idx->last_slot * NQ_MAX, NQ_MAX * 4, cudaMemcpyDeviceToHost));
+    NAFP_CUDA(cudaMemcpy(cnt.data(), idx->cnt + static_cast<size_t>(idx->last_slot) * cnt.size(), cnt.size() * 4, cudaMemcpyDeviceToHost));
     for (int q = 0; q < NQ_MAX; ++q) {
         int32_t o = tg[q];
         uint32_t b = static_cast<uint32_t>(o >= 0 ? o : (o ^ 0x7FFFFFFF));

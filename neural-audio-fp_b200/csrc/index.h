@@ -16,7 +16,8 @@ constexpr int POOL_CAP = 128;        // candidate slots per (CTA, query) per pas
 constexpr int MAX_K = 128;
 constexpr int BRUTE_CHUNKS = 296;        // CTAs per query of the exact fallback scan (2 per SM)
 constexpr int BRUTE_SLOTS = 32;          // queries per fallback launch
-constexpr int SELECT_CAP = 4096;     // candidates re-ranked in fp32 per query, at most
+constexpr int SELECT_CAP = 4096;
+constexpr int SEL_SLOTS = 16;        // scan passes whose survivors are re-ranked by ONE flat_select launch     // candidates re-ranked in fp32 per query, at most
 
 struct IvfPq;                        // ivfpq.cu
 
@@ -39,7 +40,8 @@ struct nafp_index {
     CUtensorMap tmap_q;
     bool tmap_db_valid = false;
 
-    // per-pass scratch (allocated on first search)
+    // per-pass scratch (allocated on first search); q32 .. gidx hold SEL_SLOTS passes
+    int last_slot = 0;
     bool scratch_ready = false;
     int grid = 0;
     __nv_bfloat16* qbf = nullptr;     // [NQ_MAX][d]
