@@ -63,40 +63,16 @@ __global__ void flat_fill_kernel(float* hn, int64_t from, int64_t to, float v) {
     if (i < to) hn[i] = v;
 }
 
-// one warp per scan tile: min and max of 0.5|x|^2 over the tile's stored rows.  min offsets the scan's
-// prefilter, max turns a tile's largest dot product into a lower bound of its largest score.
-__global__ void flat_tile_hmin_kernel(const float* __restrict__ hn, float2* __restrict__ tile_h, int64_t tile_first,
-                                      int64_t n_tiles, int64_t n_rows) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_tiles) return;
-    const int64_t t = tile_first + w;
-    float m = INFINITY, M = 0.f;
-    for (int j = lane; j < SCAN_TILE; j += 32) {
-        const int64_t r = t * SCAN_TILE + j;
-        if (r < n_rows) {
-            const float h = hn[r];
-            m = fminf(m, h);
-            M = fmaxf(M, h);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
-    }
-    if (lane == 0) tile_h[t] = make_float2(m, M);
-}
-
 // one warp per query row of the pass (rows >= nq are zero padding).  The pass takes rows
 // p0 .. p0+nq-1 of q_all, or -- for a retry pass -- the rows listed in src_list[src_off ..].
 __global__ void flat_prep_kernel(const float* __restrict__ q_all, const int32_t* __restrict__ src_list, int src_off,
                                  int64_t p0, int nq, int nq_pad, int grid_scan,
                                  __nv_bfloat16* __restrict__ qbf, float* __restrict__ q32,
                                  float* __restrict__ qn2, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg,
-                                 int32_t* __restrict__ flags, int64_t* __restrict__ gidx) {
+                                 int32_t* __restrict__ flags, int64_t* __restrict__ gidx, int32_t* __restrict__ tile_counter) {
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;      // the scan's dynamic tile scheduler
     if (row >= nq_pad) return;
     int64_t g = -1;
     if (row < nq) g = src_list ? static_cast<int64_t>(src_list[src_off + row]) : p0 + row;
@@ -148,6 +124,7 @@ struct ScanBars {
     uint64_t qfull;
     uint32_t tmem_base;
     int done;          // epilogue warps that finished
+    int tile_of[8];    // work item i (mod 8) -> DB tile, -1 = no more work (written by the TMA producer)
 };
 
 __device__ __forceinline__ void smem_red_max(int* p, int v) {
@@ -192,10 +169,10 @@ __device__ __forceinline__ void scan_append(float v, float h, float t_exact, uin
 // DB rows of the tile.  An epilogue thread therefore owns one query per 128-query half: its
 // threshold is ONE register, and the hot loop is a 3-input max over the columns followed by a single
 // compare -- no per-score add, no threshold traffic.  -0.5|x|^2 enters the prefilter through the
-// tile's minimum (tile_hmin) and is applied exactly only to the few scores that pass it.
+// minimum over the warp's 64 rows and is applied exactly only to the few scores that pass it.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                 const float* __restrict__ hn, const float2* __restrict__ tile_h, int64_t n_search, int n_tiles, int nq,
+                 const float* __restrict__ hn, int32_t* __restrict__ tile_counter, int64_t n_search, int n_tiles, int nq,
                  int n_half, int kg, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
                  int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first) {
     extern __shared__ uint8_t smem_raw[];
@@ -211,10 +188,10 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int G = gridDim.x;
     const int cta = blockIdx.x;
-    // tiles are dealt round-robin (tile = cta + i G): rows that many queries match -- the reference appends
-    // the real database after the dummy one -- are spread over all CTAs instead of loading the last few
-    const int n_own = (n_tiles - cta + G - 1) / G;
-    // Iterations 0..n_own-1 visit the CTA's tiles once, iteration n_own re-visits tile 0 (see the epilogue).
+    // Work items of a CTA: tile `cta` (scanned max-only), then tiles handed out by a global counter
+    // (SMs do not all stream at the same rate: with a static split the slowest CTA finished 35 % after the
+    // fastest), then tile `cta` again (with thresholds), then the end marker.  The TMA producer draws the
+    // tiles and tells the MMA issuer and the epilogue through bars->tile_of.
 
     for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
         lmax_s[i] = INT_MIN;
@@ -252,24 +229,41 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int kb = 0; kb < 2; ++kb)
                 for (int r0 = 0; r0 < q_rows; r0 += 32)
                     tma_load_2d(q_s + kb * Q_KB_BYTES + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
-            const int n_iter = n_own + 1;          // tile 0 is visited twice (max-only, then with thresholds)
-            for (int i = 0; i < n_iter; ++i) {
-                const int tile = i < n_own ? cta + i * G : cta;
+            int tile = cta;
+            bool revisited = false;
+            int nxt = G + atomicAdd(tile_counter, 1);           // drawn one item ahead: the round trip hides behind the loads
+            for (int i = 0;; ++i) {
+                const int kc0 = 2 * i;
+                const uint32_t ph = (kc0 / RING_SLOTS) & 1;
+                const int s0 = kc0 % RING_SLOTS;
+                mbar_wait_parked(&bars->empty[s0], ph ^ 1);
+                bars->tile_of[i & 7] = tile;                      // released to the consumers by the arrive below
+                if (tile < 0) {
+                    mbar_arrive(&bars->full[s0]);
+                    break;
+                }
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
-                    const int kc = 2 * i + kb;
-                    const int s = kc % RING_SLOTS;
-                    const uint32_t ph = (kc / RING_SLOTS) & 1;
-                    mbar_wait_parked(&bars->empty[s], ph ^ 1);
+                    const int s = s0 + kb;
+                    if (kb == 1) mbar_wait_parked(&bars->empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&bars->full[s], SLOT_BYTES + (kb == 0 ? SCAN_TILE * 4 : 0));
                     // the tile's 0.5|x|^2 travel with its first K block.  Ring of 4: entry i is rewritten for
-                    // tile i+4, whose load is issued after tile i+2's MMAs, which start after tile i's epilogue
+                    // item i+4, whose load is issued after item i+2's MMAs, which start after item i's epilogue
                     if (kb == 0)
                         bulk_load_1d(h_s + (i % H_RING) * SCAN_TILE, hn + static_cast<int64_t>(tile) * SCAN_TILE, SCAN_TILE * 4,
                                      &bars->full[s]);
                     uint8_t* dst = b_s + s * SLOT_BYTES;
                     tma_load_2d(dst, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE);
                     tma_load_2d(dst + BOX_BYTES, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE + TILE_ROWS);
+                }
+                if (revisited) {
+                    tile = -1;
+                } else if (nxt < n_tiles) {
+                    tile = nxt;
+                    nxt = G + atomicAdd(tile_counter, 1);
+                } else {
+                    tile = cta;
+                    revisited = true;
                 }
             }
         }
@@ -285,9 +279,9 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint64_t adesc0 = umma_desc_sw128(smem_u32(q_s));
         const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_s));
         mbar_wait_parked(&bars->qfull, 0);
-        const int n_iter = n_own + 1;
         uint32_t uc = 0;
-        for (int i = 0; i < n_iter; ++i) {
+        bool more = true;
+        for (int i = 0; more; ++i) {
             const int s0 = (2 * i) % RING_SLOTS, s1 = s0 + 1;
             const uint32_t ph = ((2 * i) / RING_SLOTS) & 1;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
@@ -295,7 +289,15 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const uint32_t aph = (uc >> 1) & 1;
                 const bool last = hq == n_half - 1;
                 mbar_wait_parked(&bars->tempty[acc], aph ^ 1);
-                if (hq == 0) mbar_wait_parked(&bars->full[s0], ph);
+                if (hq == 0) {
+                    mbar_wait_parked(&bars->full[s0], ph);
+                    if (smem_ld_volatile(&bars->tile_of[i & 7]) < 0) {      // end marker: wake the epilogue and stop
+                        if (leader) tc_commit(&bars->tfull[acc]);
+                        __syncwarp();
+                        more = false;
+                        break;
+                    }
+                }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * SCAN_TILE;
                 const uint64_t a_kb0 = adesc0 + static_cast<uint64_t>((hq * (128 * 128)) >> 4);
@@ -376,12 +378,6 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             }
         };
-        // Tile 0 is scanned "max-only": it feeds the running maxima from which the shared thresholds
-        // are built.  The warp then waits (bounded) for the thresholds of its queries and scans
-        // everything else in normal mode; tile 0 is re-visited at the end (iteration n_own).
-        const int n_iter = n_own + 1;
-        uint32_t uc = 0;
-        float2 h_next = __ldg(tile_h + cta);
         // developer probe (nq <= 248): ns since kernel start at which tile 0 / the threshold wait / the scan ended
         const bool probe = dbg_first != nullptr && threadIdx.x == 0 && nq <= 248;
         unsigned long long t_start = 0;
@@ -393,63 +389,84 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 dbg_first[cta * NQ_MAX + 248 + slot] = static_cast<int>(t - t_start);
             }
         };
-        for (int i = 0; i < n_iter; ++i) {
-            if (i == 1) stamp(0);
-            if (i == 2) stamp(2);
-            if (i == n_own) stamp(3);
-            const bool maxonly = i == 0;
-            const int tile = i < n_own ? cta + i * G : cta;
-            const float2 h_t = h_next;     // {min, max} of 0.5|x|^2 over the tile
-            {
-                const int tnext = i + 1 < n_own ? tile + G : cta;
-                h_next = __ldg(tile_h + tnext);
-            }
-            int tg[2] = {INT_MIN, INT_MIN};
-            const bool rf = i > 1 && (i < 32 || (i & 3) == 0);      // loads issued now, consumed after the tile
-            if (i == 1) {
-                bool ok = false;
-                for (int spin = 0; spin < 4096 && !ok; ++spin) {
-                    publish_maxima();          // the other warps' tile-0 maxima of the queries this warp publishes
-                    load_thresholds(tg);
-                    ok = apply_thresholds(tg, i);
-                    if (!ok) __nanosleep(100);
-                }
-                // not ok after ~0.5 ms: scan on with -inf thresholds; the pools overflow and the exact
-                // fallback answers those queries
-                stamp(1);
-            } else if (rf) {
-                load_thresholds(tg);
-            }
-            const uint32_t row0 = static_cast<uint32_t>(tile) * SCAN_TILE + part * PART_COLS;
-            // prefilter: s = v - h > T  implies  v > T + min_tile(h) (minus a rounding margin)
-            const float hm = h_t.x * (1.f - 1.f / 1048576.f);
-            // max-only: max_j v_j - max_tile(h) is a lower bound of the tile's best score, good enough for
-            // the running maxima; only a tile with halo / padding rows needs the exact per-row form
-            const bool whole = static_cast<uint32_t>(tile + 1) * SCAN_TILE <= ns32;
-            const float hM = h_t.y * (1.f + 1.f / 1048576.f);
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + part * PART_COLS;
+        uint32_t uc = 0;
+
+        // ---- item 0 (tile `cta`) is scanned "max-only": its exact scores feed the running maxima from
+        // which the shared thresholds are built; the tile comes back with thresholds as the last item.
+        {
+            const uint32_t row0 = static_cast<uint32_t>(cta) * SCAN_TILE + part * PART_COLS;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
-                const uint32_t aph = (uc >> 1) & 1;
-                const int q = hq * 128 + qd * 32 + lane;
-                const bool act = hq == 0 ? active[0] : active[1];
-                const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
-                mbar_wait(&bars->tfull[acc], aph);
+                mbar_wait(&bars->tfull[acc], (uc >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * SCAN_TILE + part * PART_COLS;
                 float munit = NEG_INF;
+#pragma unroll 1
+                for (int c = 0; c < PART_COLS / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tlane + acc * SCAN_TILE + c * 32, v);
+                    tc_wait_ld();
+                    const float* hc = h_s + part * PART_COLS + c * 32;          // h ring entry 0
+                    const int nvalid = static_cast<int>(min(ns32 - min(ns32, row0 + c * 32), 32u));   // rows < n_search
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nvalid) munit = fmaxf(munit, __uint_as_float(v[j]) - hc[j]);
+                }
+                if (hq == 0 ? active[0] : active[1]) smem_red_max(&lmax_s[hq * 128 + qd * 32 + lane], f2ord(munit));
+                tc_fence_before();
+                __syncwarp();
+                mbar_arrive_lane0(&bars->tempty[acc], lane);
+            }
+            publish_maxima();
+            stamp(0);
+        }
+        // ---- wait (bounded) for the thresholds of this warp's queries
+        {
+            int tg[2];
+            bool ok = false;
+            for (int spin = 0; spin < 4096 && !ok; ++spin) {
+                publish_maxima();          // the other warps' tile-0 maxima of the queries this warp publishes
+                load_thresholds(tg);
+                ok = apply_thresholds(tg, 1);
+                if (!ok) __nanosleep(100);
+            }
+            // not ok after ~0.5 ms: scan on with -inf thresholds; the pools overflow and the exact fallback
+            // answers those queries
+            stamp(1);
+        }
+        // ---- the items the producer draws for this CTA, ending with tile `cta` again and the end marker
+        for (int i = 1;; ++i) {
+            int tg[2] = {INT_MIN, INT_MIN};
+            const bool rf = i > 1 && (i < 32 || (i & 3) == 0);      // loads issued now, consumed after the tile
+            if (rf) load_thresholds(tg);
+            const float* h_part = h_s + (i % H_RING) * SCAN_TILE + part * PART_COLS;
+            uint32_t row0 = 0;
+            float hm = 0.f;
+            bool end = false;
+            for (int hq = 0; hq < n_half; ++hq, ++uc) {
+                const int acc = uc & 1;
+                mbar_wait(&bars->tfull[acc], (uc >> 1) & 1);
+                if (hq == 0) {
+                    const int tile = smem_ld_volatile(&bars->tile_of[i & 7]);
+                    if (tile < 0) {
+                        end = true;
+                        break;
+                    }
+                    row0 = static_cast<uint32_t>(tile) * SCAN_TILE + part * PART_COLS;
+                    // prefilter offset: s = v - h > T implies v > T + min(h) over this warp's 64 rows (minus a
+                    // rounding margin); the rows' 0.5|x|^2 arrived in shared memory with the tile
+                    const float hmin_w =
+                        __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(h_part[lane], h_part[32 + lane]))));
+                    hm = hmin_w * (1.f - 1.f / 1048576.f);
+                }
+                const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
+                tc_fence_after();
+                const uint32_t taddr = tlane + acc * SCAN_TILE;
 #pragma unroll 1
                 for (int c = 0; c < PART_COLS / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + c * 32, v);
                     tc_wait_ld();
-                    const float* hc = h_s + (i % H_RING) * SCAN_TILE + part * PART_COLS + c * 32;    // h of this chunk's rows
-                    if (maxonly && !whole) {
-                        const uint32_t r = row0 + c * 32 + lane;
-                        const float h = r < ns32 ? hc[lane] : INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) munit = fmaxf(munit, __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, h, j));
-                        continue;
-                    }
                     // maxima of the four 8-column groups (FMNMX3), then of the chunk
                     float gm[4];
 #pragma unroll
@@ -460,16 +477,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
                     }
                     const float ma = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
-                    if (maxonly) {
-                        munit = fmaxf(munit, ma - hM);
-                        continue;
-                    }
                     const bool fired = ma > tp;
                     if (__any_sync(0xffffffffu, fired)) {
                         // rare: this lane's query has a score above the prefilter among the 32 columns;
                         // only the 8-column groups whose maximum fired are looked at
                         if (fired) {
+                            const int q = hq * 128 + qd * 32 + lane;
                             const float te = hq == 0 ? t_exact[0] : t_exact[1];
+                            const float* hc = h_part + c * 32;
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 if (gm[g] > tp) {
@@ -484,14 +499,17 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         __syncwarp();
                     }
                 }
-                if (maxonly && act) smem_red_max(&lmax_s[q], f2ord(munit));
                 tc_fence_before();
                 __syncwarp();
                 mbar_arrive_lane0(&bars->tempty[acc], lane);
             }
+            if (end) break;
             if (rf) apply_thresholds(tg, i);
-            if (i < 32 || (i & 3) == 0 || i >= n_own - 1) publish_maxima();
+            if (i < 32 || (i & 3) == 0) publish_maxima();
+            if (i == 1) stamp(2);
         }
+        stamp(3);
+        publish_maxima();
         stamp(4);
         __syncwarp();
         // all epilogue warps are done appending before counts are published
@@ -830,8 +848,6 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     float* x32 = nullptr;
     __nv_bfloat16* x16 = nullptr;
     float* hn = nullptr;
-    float2* tile_hmin = nullptr;
-    NAFP_CUDA(cudaMalloc(&tile_hmin, static_cast<size_t>(new_cap / SCAN_TILE + 2) * sizeof(float2)));
     NAFP_CUDA(cudaMalloc(&x32, static_cast<size_t>(new_cap) * idx->d * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&x16, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16)));
     NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap + SCAN_TILE) * sizeof(float)));
@@ -842,8 +858,6 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
         NAFP_CUDA(cudaMemcpyAsync(x16, idx->x16, static_cast<size_t>(idx->n) * idx->d * sizeof(__nv_bfloat16),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
         NAFP_CUDA(cudaMemcpyAsync(hn, idx->hn, static_cast<size_t>(idx->n) * sizeof(float),
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
-        NAFP_CUDA(cudaMemcpyAsync(tile_hmin, idx->tile_hmin, static_cast<size_t>((idx->n + SCAN_TILE - 1) / SCAN_TILE) * sizeof(float2),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     }
     {
@@ -858,8 +872,6 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     if (idx->x32) cudaFree(idx->x32);
     if (idx->x16) cudaFree(idx->x16);
     if (idx->hn) cudaFree(idx->hn);
-    if (idx->tile_hmin) cudaFree(idx->tile_hmin);
-    idx->tile_hmin = tile_hmin;
     idx->x32 = x32;
     idx->x16 = x16;
     idx->hn = hn;
@@ -890,12 +902,7 @@ int flat_add_dev(nafp_index* idx, const float* x, int64_t n, bool src_is_host) {
     if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
     flat_convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(idx->x32, idx->x16, idx->hn,
                                                                                         idx->maxn2, idx->n, n);
-    {
-        const int64_t tf = idx->n / SCAN_TILE, tl = (idx->n + n - 1) / SCAN_TILE;
-        flat_tile_hmin_kernel<<<static_cast<unsigned>(((tl - tf + 1) * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
-            idx->hn, idx->tile_hmin, tf, tl - tf + 1, idx->n + n);
-    }
-    ctx->launches += 2;
+    ctx->launches++;
     NAFP_CUDA(cudaGetLastError());
     if (src_is_host) NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     idx->n += n;
@@ -919,6 +926,7 @@ static int ensure_scratch(nafp_index* idx) {
     NAFP_CUDA(cudaMalloc(&idx->gidx, SEL_SLOTS * NQ_MAX * sizeof(int64_t)));
     NAFP_CUDA(cudaMalloc(&idx->brute_part, static_cast<size_t>(BRUTE_SLOTS) * BRUTE_CHUNKS * MAX_K * sizeof(uint64_t)));
     NAFP_CUDA(cudaMalloc(&idx->stats, 8 * sizeof(unsigned long long)));
+    NAFP_CUDA(cudaMalloc(&idx->tile_counter, sizeof(int32_t)));
     NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
     const uint64_t dims[2] = {static_cast<uint64_t>(D128), static_cast<uint64_t>(NQ_MAX)};
     const uint64_t strides[2] = {2, static_cast<uint64_t>(D128) * 2};
@@ -959,10 +967,10 @@ static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_lis
     int32_t* flags = idx->flags + slot * NQ_MAX;
     int64_t* gidx = idx->gidx + slot * NQ_MAX;
     flat_prep_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, ctx->stream>>>(q_dev, src_list, src_off, p0, np, nq_pad, grid_scan,
-                                                                         idx->qbf, q32, qn2, idx->Mx, Tg, flags, gidx);
+                                                                         idx->qbf, q32, qn2, idx->Mx, Tg, flags, gidx, idx->tile_counter);
     const bool prof = idx->profile && idx->prof_n < PROF_RING;
     if (prof) cudaEventRecord(idx->prof_ev[2 * idx->prof_n], ctx->stream);
-    flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, idx->tile_hmin, n_search,
+    flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, idx->tile_counter, n_search,
                                                                           n_tiles, np, n_half, kg, idx->Mx, Tg, pool, cnt, flags,
                                                                           idx->dbg_first);
     if (prof) {
@@ -1097,7 +1105,7 @@ int nafp_index_destroy(nafp_index* idx) {
     cudaStreamSynchronize(idx->ctx->stream);
     if (idx->ivf) ivfpq_destroy(idx);
     for (auto& e : idx->prof_ev) cudaEventDestroy(e);
-    void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->tile_hmin, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
+    void* bufs[] = {idx->x32, idx->x16, idx->hn, idx->tile_counter, idx->maxn2, idx->qbf, idx->q32, idx->qn2, idx->Mx, idx->Tg,
                     idx->pool, idx->cnt, idx->flags, idx->gidx, idx->fail_list, idx->brute_part, idx->stats, idx->dbg_first, idx->stage_q, idx->stage_D,
                     idx->stage_I};
     for (void* b : bufs)

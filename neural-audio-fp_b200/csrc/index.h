@@ -32,7 +32,6 @@ struct nafp_index {
     float* x32 = nullptr;             // [cap][d] exact rows (re-rank, reconstruct, sequence scoring)
     __nv_bfloat16* x16 = nullptr;     // [cap][d] scan copy
     float* hn = nullptr;              // [cap + SCAN_TILE] 0.5*|x|^2, +inf for unused rows
-    float2* tile_hmin = nullptr;      // [cap / SCAN_TILE + 2] {min, max} of hn over each scan tile
     int32_t* maxn2 = nullptr;         // device scalar: bits of max |x|^2 (non-negative float)
     int64_t label_offset = 0;
     int64_t search_rows = -1;     // leading rows that take part in search (-1 = all); the rest are halo
@@ -57,6 +56,7 @@ struct nafp_index {
     int64_t fail_cap = 0;
     uint64_t* brute_part = nullptr;   // [BRUTE_SLOTS][BRUTE_CHUNKS][MAX_K]
     unsigned long long* stats = nullptr;   // [8] device counters
+    int32_t* tile_counter = nullptr;  // device scalar: next DB tile the scan's producers draw
     int32_t* dbg_first = nullptr;     // developer probe: [grid][NQ_MAX] tile index of the first shared threshold
     // staging for the host entry points
     float* stage_q = nullptr;  int64_t stage_q_rows = 0;

@@ -30,3 +30,7 @@ for rep in range(2):
     print("rep", rep, "G", G, "ns since start: tile0 done / thresholds ok / tile1 done / own tiles done / end")
     print(" median", np.median(t, 0).tolist(), " min", t.min(0).tolist(), " max", t.max(0).tolist())
     print(" survivors per CTA-query: mean", cnt[:, :nq].mean(), "max", cnt[:, :nq].max())
+    own = t[:, 3]
+    order = np.argsort(own)
+    print(" own-tiles-done ns by CTA (sorted): fastest", [(int(c), int(own[c])) for c in order[:6]], "slowest", [(int(c), int(own[c])) for c in order[-10:]])
+    print(" survivors per CTA (sum over queries): slowest", [int(cnt[c, :nq].sum()) for c in order[-10:]], "fastest", [int(cnt[c, :nq].sum()) for c in order[:6]], "corr", float(np.corrcoef(own, cnt[:, :nq].sum(1))[0, 1]))
