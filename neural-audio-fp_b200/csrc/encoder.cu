@@ -113,7 +113,14 @@ static void build_geometry(ConvGeom* g) {
     }
 }
 
-__device__ __forceinline__ float elu(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// ELU(v) = v > 0 ? v : e^v - 1.  Only the v <= 0 side reaches the exponential, where e^v is in (0, 1]: the bare
+// MUFU ex2 (flush-to-zero) is exact enough (2 ulp, absolute error 2^-22 after the -1) and saves the
+// denormal-range fix-up of __expf -- 5 of the ~15 instructions per output element of the conv epilogues.
+__device__ __forceinline__ float elu(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    return v > 0.f ? v : e - 1.f;
+}
 
 // ------------------------------------------------------------------------------------------
 // conv0_a: (B,256,32) fp32 log-mel -> (B,256,16,128) normalised fp16, stride 2 in time, pad (0,1).
@@ -134,22 +141,9 @@ __device__ __forceinline__ void conv0_load_lane(const float* __restrict__ w0, co
     const float4 v = reinterpret_cast<const float4*>(b0)[lane];
     L.bia[0] = v.x; L.bia[1] = v.y; L.bia[2] = v.z; L.bia[3] = v.w;
 }
-// ELU(conv) of the lane's 4 channels at position p (= f * 16 + t') of one segment
-__device__ __forceinline__ void conv0_point(const float* __restrict__ m, int p, bool raw, float sub, const Conv0Lane& L,
-                                            float (&o)[4]) {
-    const int f = p >> 4, tp = p & 15;
-    float xv[3];
-#pragma unroll
-    for (int tap = 0; tap < 3; ++tap) {
-        const int t = 2 * tp + tap;
-        float v = t < 32 ? __ldg(m + f * 32 + t) : 0.f;
-        if (raw && t < 32) v = fmaxf(v - sub, -80.f);       // "- batch max, clamp -80" (melspectrogram.py:108-109)
-        xv[tap] = v;
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) o[c] = elu(L.bia[c] + xv[0] * L.w[0][c] + xv[1] * L.w[1][c] + xv[2] * L.w[2][c]);
-}
-
+// Block (bx, seg): frequency rows 32 bx .. 32 bx + 31 of one segment; a warp takes rows warp, warp + 8, ...:
+// the row's 32 log-mel values are one coalesced load, the three taps of every output position come from
+// warp shuffles, and the 16 positions of the row are unrolled so that the stores use immediate offsets.
 __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int n_seg,
              const float* __restrict__ w0, const float* __restrict__ b0, __half* __restrict__ y,
@@ -163,23 +157,37 @@ conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, in
     const float* m = mel + static_cast<int64_t>(seg) * 8192;
     __half* out = y + static_cast<int64_t>(seg) * (256 * 16 * 128);
     float s1 = 0.f, s2 = 0.f;
-    for (int p = blockIdx.x * 512 + warp; p < (blockIdx.x + 1) * 512; p += 8) {      // 8 blocks x 512 positions
-        float o[4];
-        conv0_point(m, p, raw, sub, L, o);
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        const int f = blockIdx.x * 32 + r * 8 + warp;
+        float v = __ldg(m + f * 32 + lane);
+        if (raw) v = fmaxf(v - sub, -80.f);                 // "- batch max, clamp -80" (melspectrogram.py:108-109)
+        uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(f) * (16 * 128)) + lane;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { s1 += o[c]; s2 += o[c] * o[c]; }
-        __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        reinterpret_cast<uint2*>(out + static_cast<int64_t>(p) * 128)[lane] = pk;
+        for (int tp = 0; tp < 16; ++tp) {
+            const float x0 = __shfl_sync(0xffffffffu, v, 2 * tp);
+            const float x1 = __shfl_sync(0xffffffffu, v, 2 * tp + 1);
+            const float x2 = tp < 15 ? __shfl_sync(0xffffffffu, v, (2 * tp + 2) & 31) : 0.f;      // SAME padding (0, 1)
+            float o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                o[c] = elu(L.bia[c] + x0 * L.w[0][c] + x1 * L.w[1][c] + x2 * L.w[2][c]);
+                s1 += o[c];
+                s2 += o[c] * o[c];
+            }
+            __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            orow[tp * 32] = pk;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0)      // one slot per (segment, block, warp): summed in fixed order by ln_stats_kernel
+    if (lane == 0)      // one slot per (segment, block, warp): summed in fixed order by ln_apply_kernel
         reinterpret_cast<float2*>(part)[static_cast<int64_t>(seg) * 64 + blockIdx.x * 8 + warp] = make_float2(s1, s2);
 }
 
@@ -364,52 +372,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// per-segment (sum, sum of squares) from the partial slots, fixed summation order; one warp per segment
-__global__ void __launch_bounds__(256)
-ln_stats_kernel(const float* __restrict__ part, int slots, int n_seg, float* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (seg >= n_seg) return;
-    const float2* p = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(seg) * slots;
-    double a = 0.0, b = 0.0;
-    for (int i = lane; i < slots; i += 32) {
-        const float2 v = p[i];
-        a += v.x;
-        b += v.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (lane == 0) {
-        stats[2 * seg] = static_cast<float>(a);
-        stats[2 * seg + 1] = static_cast<float>(b);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // LayerNorm over (F,T,C) with per-element gamma/beta: 8 elements per thread
 // ------------------------------------------------------------------------------------------
 constexpr int LN_SEGS = 8;         // segments per thread: gamma/beta (8 B per element) are loaded once for all of them
+static_assert(LN_SEGS == 8, "ln_apply_kernel maps its 8 warps to the block's segments");
+// The block first reduces the (sum, sum of squares) partial slots of its 8 segments -- one warp per segment,
+// fixed order, double accumulation: bit-reproducible and no separate statistics launch.
 __global__ void __launch_bounds__(256)
-ln_apply_kernel(const __half* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, __half* __restrict__ x, int per_seg, int n_seg) {
+ln_apply_kernel(const __half* __restrict__ y, const float* __restrict__ part, int slots, float* __restrict__ stats_out,
+                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ x, int per_seg, int n_seg) {
+    __shared__ float2 mr_s[LN_SEGS];          // (mean, rstd) of the block's segments
+    const int seg0 = blockIdx.y * LN_SEGS;
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;      // 8 warps = LN_SEGS segments
+        const int seg = seg0 + w;
+        if (seg < n_seg) {
+            const float2* p = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(seg) * slots;
+            double a = 0.0, b = 0.0;
+            for (int i = lane; i < slots; i += 32) {
+                const float2 v = p[i];
+                a += v.x;
+                b += v.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) {
+                const float inv_n = 1.f / static_cast<float>(per_seg);
+                const float s1 = static_cast<float>(a), s2 = static_cast<float>(b);
+                const float mean = s1 * inv_n;
+                const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+                mr_s[w] = make_float2(mean, rsqrtf(var + LN_EPS));
+                if (blockIdx.x == 0 && stats_out) {
+                    stats_out[2 * seg] = s1;
+                    stats_out[2 * seg + 1] = s2;
+                }
+            }
+        }
+    }
+    __syncthreads();
     const int off = (blockIdx.x * blockDim.x + threadIdx.x) * 8;        // 8 consecutive elements of the (F,T,C) volume
     if (off >= per_seg) return;
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + off), g1 = *reinterpret_cast<const float4*>(gamma + off + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(beta + off), b1 = *reinterpret_cast<const float4*>(beta + off + 4);
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float inv_n = 1.f / static_cast<float>(per_seg);
-    const int seg0 = blockIdx.y * LN_SEGS;
 #pragma unroll 4
     for (int k = 0; k < LN_SEGS; ++k) {
         const int b = seg0 + k;
         if (b >= n_seg) break;
-        const float mean = stats[2 * b] * inv_n;
-        const float var = fmaxf(stats[2 * b + 1] * inv_n - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + LN_EPS);
+        const float mean = mr_s[k].x, rstd = mr_s[k].y;
         const int64_t idx = static_cast<int64_t>(b) * per_seg + off;
         const uint4 raw = *reinterpret_cast<const uint4*>(y + idx);
         const __half2* hv = reinterpret_cast<const __half2*>(&raw);
@@ -576,10 +591,9 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
         const int per = L.ms * L.c_out;
         if (l == 0) {
             conv0_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, n, s->w0, s->bias[0], s->y, s->part);
-            ln_stats_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->part, 64, n, stats);
             ln_apply_kernel<<<dim3((per / 8 + 255) / 256, (n + LN_SEGS - 1) / LN_SEGS), 256, 0, st>>>(
-                s->y, stats, s->ln_g[0], s->ln_b[0], s->x[0], per, n);
-            ctx->launches += 3;
+                s->y, s->part, 64, stats, s->ln_g[0], s->ln_b[0], s->x[0], per, n);
+            ctx->launches += 2;
             continue;
         }
         ConvParams p;
@@ -592,10 +606,9 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
         const int tiles = p.n_mtiles * p.n_ntiles;
         const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
         conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, s->part);
-        ln_stats_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->part, slots, n, stats);
         ln_apply_kernel<<<dim3((per / 8 + 255) / 256, (n + LN_SEGS - 1) / LN_SEGS), 256, 0, st>>>(
-            s->y, stats, s->ln_g[l], s->ln_b[l], s->x[l], per, n);
-        ctx->launches += 3;
+            s->y, s->part, slots, stats, s->ln_g[l], s->ln_b[l], s->x[l], per, n);
+        ctx->launches += 2;
     }
     divenc_kernel<<<dim3(EMB, (n + 127) / 128), 128, 0, st>>>(s->x[ENC_LAYERS - 1], n, s->dw1, s->db1, s->dw2, s->db2, s->raw);
     l2norm_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(s->raw, n, emb_dev);
