@@ -195,7 +195,9 @@ conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, in
 // implicit-GEMM separable convolution on tcgen05
 // ------------------------------------------------------------------------------------------
 constexpr int CONV_STAGES = 4;
-constexpr int CONV_THREADS = 320;          // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue
+constexpr int CONV_EPI_WARPS = 16;         // 4 per TMEM lane quadrant: each takes a quarter of the tile's columns
+constexpr int CONV_EPI_PARTS = CONV_EPI_WARPS / 4;
+constexpr int CONV_THREADS = (2 + CONV_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2.. epilogue
 constexpr int CONV_A_BYTES = 128 * 128;    // 128 rows x 64 fp16
 constexpr int CONV_B_BYTES_MAX = 256 * 128;
 constexpr int CONV_SMEM = CONV_STAGES * (CONV_A_BYTES + CONV_B_BYTES_MAX) + 1024 * 4 + 256 + 1024;
@@ -205,6 +207,7 @@ struct ConvBars {
     uint64_t empty[CONV_STAGES];
     uint64_t tfull[2];
     uint64_t tempty[2];
+    uint64_t bfull;            // resident-weights mode: all K blocks of the CTA's N tile have landed
     uint32_t tmem_base;
 };
 
@@ -224,6 +227,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_tiles = p.n_mtiles * p.n_ntiles;
     const int n_taps = p.tap_hi - p.tap_lo + 1;
     const int k_iters = n_taps * p.kb_per_tap;
+    // Weights resident: when all K blocks of one N tile fit into the B ring's space (<= 128 KB: the three
+    // 128-channel layers, 96 KB) and every tile of this CTA has the same N tile, B is loaded ONCE and only
+    // A streams -- half the TMA / L2 traffic of those layers.
+    const bool b_resident = k_iters * b_bytes <= CONV_STAGES * CONV_B_BYTES_MAX && gridDim.x % p.n_ntiles == 0;
 
     for (int i = threadIdx.x; i < p.c_out; i += blockDim.x) bias_s[i] = bias[i];
     if (threadIdx.x == 0) {
@@ -235,8 +242,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tfull[a], 1);
-            mbar_init(&bars->tempty[a], 8);
+            mbar_init(&bars->tempty[a], CONV_EPI_WARPS);
         }
+        mbar_init(&bars->bfull, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -246,12 +254,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);     // provably warp-uniform
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int it = 0;
+            if (b_resident && static_cast<int>(blockIdx.x) < n_tiles) {
+                const int n0 = (blockIdx.x % p.n_ntiles) * p.nt;
+                mbar_arrive_expect_tx(&bars->bfull, static_cast<uint32_t>(k_iters * b_bytes));
+                int k = 0;
+                for (int tap = p.tap_lo; tap <= p.tap_hi; ++tap)
+                    for (int kb = 0; kb < p.kb_per_tap; ++kb, ++k)
+                        tma_load_2d(b_s + k * b_bytes, &tmB, &bars->bfull, tap * p.c_in + kb * 64, n0);
+            }
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_ntiles, ntile = tile % p.n_ntiles;
                 int b0, f0;
@@ -263,7 +279,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int s = it % CONV_STAGES;
                         const uint32_t ph = (it / CONV_STAGES) & 1;
                         mbar_wait(&bars->empty[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&bars->full[s], CONV_A_BYTES + b_bytes);
+                        mbar_arrive_expect_tx(&bars->full[s], CONV_A_BYTES + (b_resident ? 0 : b_bytes));
                         uint8_t* da = a_s + s * CONV_A_BYTES;
                         const int c0 = kb * 64;
                         // mode 0: (c,t,f,b)        time conv, unit stride in the box: t = tap - pad
@@ -274,7 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         else if (p.mode == 1) tma_load_5d(da, &tmA, &bars->full[s], c0, tap & 1, tap >> 1, f0, b0);
                         else if (p.mode == 2) tma_load_5d(da, &tmA, &bars->full[s], c0, 0, tap & 1, f0 + (tap >> 1), b0);
                         else                  tma_load_4d(da, &tmA, &bars->full[s], c0, 0, f0 + tap - p.pad_lo, b0);
-                        tma_load_2d(b_s + s * CONV_B_BYTES_MAX, &tmB, &bars->full[s], tap * p.c_in + c0, n0);
+                        if (!b_resident) tma_load_2d(b_s + s * CONV_B_BYTES_MAX, &tmB, &bars->full[s], tap * p.c_in + c0, n0);
                     }
                 }
             }
@@ -282,37 +298,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(0u, 128, static_cast<uint32_t>(p.nt));
-            const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
-            int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-                const int acc = lt & 1;
-                const uint32_t aph = (lt >> 1) & 1;
-                mbar_wait(&bars->tempty[acc], aph ^ 1);
-                const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int k = 0; k < k_iters; ++k, ++it) {
-                    const int s = it % CONV_STAGES;
-                    const uint32_t ph = (it / CONV_STAGES) & 1;
-                    mbar_wait(&bars->full[s], ph);
-                    tc_fence_after();
+        // The whole warp runs the loop (uniform control flow: descriptors and counters stay in uniform
+        // registers, no ELECT / R2UR waterfall around every MMA); one elected lane issues.
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc_f16(0u, 128, static_cast<uint32_t>(p.nt));
+        const uint64_t adesc0 = umma_desc_sw128(smem_u32(a_s));
+        const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_s));
+        const uint32_t b_stride16 = static_cast<uint32_t>(b_resident ? b_bytes : CONV_B_BYTES_MAX) >> 4;
+        if (b_resident && static_cast<int>(blockIdx.x) < n_tiles) mbar_wait(&bars->bfull, 0);
+        int it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            mbar_wait(&bars->tempty[acc], aph ^ 1);
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int k = 0; k < k_iters; ++k, ++it) {
+                const int s = it % CONV_STAGES;
+                const uint32_t ph = (it / CONV_STAGES) & 1;
+                mbar_wait(&bars->full[s], ph);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t adesc = adesc0 + static_cast<uint64_t>((s * CONV_A_BYTES) >> 4);
+                    const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((b_resident ? k : s) * b_stride16);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint64_t adesc = umma_desc_sw128(a_addr + s * CONV_A_BYTES + j * 32);
-                        const uint64_t bdesc = umma_desc_sw128(b_addr + s * CONV_B_BYTES_MAX + j * 32);
-                        tc_mma_f16(d_tmem, adesc, bdesc, idesc, (k | j) != 0 ? 1u : 0u);
-                    }
+                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0 ? 1u : 0u);
                     tc_commit(&bars->empty[s]);
+                    if (k == k_iters - 1) tc_commit(&bars->tfull[acc]);
                 }
-                tc_commit(&bars->tfull[acc]);
+                __syncwarp();
             }
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue (8 warps)
+        // ------------------------------------------------------------ epilogue (CONV_EPI_WARPS warps)
         const int qd = warp & 3;               // TMEM lane quadrant = rows 32 qd .. 32 qd + 31 of the tile
-        const int half = (warp - 2) >> 2;      // which half of the tile's columns
-        const int cols = p.nt / 2;
+        const int half = (warp - 2) >> 2;      // which part of the tile's columns
+        const int cols = p.nt / CONV_EPI_PARTS;
         const int seg_len = p.ms < 32 ? p.ms : 32;     // rows of one segment inside this warp (power of two)
         int lt = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
@@ -361,7 +382,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (row_ok && (lane & (seg_len - 1)) == 0) {
                 const int b = m / p.ms;
                 const int grp = p.ms >= 32 ? (m % p.ms) >> 5 : 0;
-                const int64_t slot = ((static_cast<int64_t>(b) * p.groups + grp) * p.n_ntiles + ntile) * 2 + half;
+                const int64_t slot = ((static_cast<int64_t>(b) * p.groups + grp) * p.n_ntiles + ntile) * CONV_EPI_PARTS + half;
                 reinterpret_cast<float2*>(part)[slot] = make_float2(s1, s2);
             }
         }
@@ -522,7 +543,7 @@ static int encoder_init(nafp_ctx* ctx) {
     }
     NAFP_CUDA(cudaMalloc(&s->y, (static_cast<size_t>(ENC_CHUNK) * ymax + 128 * 1024) * sizeof(__half)));
     NAFP_CUDA(cudaMalloc(&s->stats, static_cast<size_t>(ENC_LAYERS) * ENC_CHUNK * 2 * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&s->part, static_cast<size_t>(ENC_CHUNK) * 128 * 2 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->part, static_cast<size_t>(ENC_CHUNK) * 64 * CONV_EPI_PARTS * 2 * sizeof(float)));   // <= 64 row groups x parts float2 slots per segment
     NAFP_CUDA(cudaMalloc(&s->dw1, 128 * 8 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->db1, 128 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->dw2, 128 * 32 * sizeof(float)));
@@ -602,7 +623,7 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
         p.mode = L.mode; p.pad_lo = L.pad_lo; p.tap_lo = L.tap_lo; p.tap_hi = L.tap_hi;
         p.kb_per_tap = L.c_in / 64; p.tps = L.ms >= 128 ? L.ms / 128 : 0; p.bf = L.bf; p.bb = L.bb;
         p.groups = L.ms >= 32 ? L.ms / 32 : 1;
-        const int slots = p.groups * p.n_ntiles * 2;
+        const int slots = p.groups * p.n_ntiles * CONV_EPI_PARTS;
         const int tiles = p.n_mtiles * p.n_ntiles;
         const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
         conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, s->part);
