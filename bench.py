@@ -347,7 +347,9 @@ def run_gpu(args):
         x_dev = torch.empty((FP_SEGS_PER_STEP, 8000), dtype=torch.float32, device=dev)
         check(lib.nafp_synth_audio(ctx.h, 5, rank * FP_SEGS_PER_STEP, FP_SEGS_PER_STEP, ctypes.c_void_p(x_dev.data_ptr())))
         emb_dev = torch.empty((FP_SEGS_PER_STEP, 128), dtype=torch.float32, device=dev)
-        x_pin = x_dev.cpu().pin_memory()
+        # e2e goes the way generate.py does: int16 PCM segments from pinned host memory (the / 2**15 of
+        # audio_utils.py:243-244 runs on the GPU), fingerprints back to host memory
+        x_pin = (x_dev.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16).cpu().pin_memory()
         emb_host = np.empty((FP_SEGS_PER_STEP, 128), np.float32)
 
         def fp_resident():
@@ -355,7 +357,7 @@ def run_gpu(args):
                                        ctypes.c_void_p(emb_dev.data_ptr())))
 
         def fp_e2e():
-            check(lib.nafp_fingerprint_host(ctx.h, ctypes.c_void_p(x_pin.data_ptr()), FP_SEGS_PER_STEP, 125,
+            check(lib.nafp_fingerprint_pcm16_host(ctx.h, ctypes.c_void_p(x_pin.data_ptr()), FP_SEGS_PER_STEP, 125,
                                             emb_host.ctypes.data_as(ctypes.c_void_p)))
 
         l0 = ctx.launches
@@ -367,7 +369,8 @@ def run_gpu(args):
         fp = {"metric": "fp_segments_per_s", "value": segs / (ms_fp * 1e-3), "unit": "segments/s", "ms_per_step": ms_fp,
               "segments_per_step": segs, "dtype": "fp16 operands, fp32 accumulate",
               "e2e": {"value": segs / (ms_fp_e2e * 1e-3), "unit": "segments/s",
-                      "h2d_bytes_per_step": FP_SEGS_PER_STEP * 32000, "d2h_bytes_per_step": FP_SEGS_PER_STEP * 512},
+                      "h2d_bytes_per_step": FP_SEGS_PER_STEP * 16000, "d2h_bytes_per_step": FP_SEGS_PER_STEP * 512,
+                      "through": "nafp_fingerprint_pcm16_host (what model/generate.py calls)"},
               "gpu_launches_per_step": int(fp_launches),
               "roofline": {"kernel": "conv_gemm_kernel (encoder, whole step)", "bound": "tensor", "achieved": tfl,
                            "peak": tf_sustained, "unit": "TFLOP/s", "frac": tfl / tf_sustained, "traffic": None,

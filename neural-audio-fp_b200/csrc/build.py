@@ -24,8 +24,6 @@ def _stale(obj, src):
 
 def build(force=False, verbose=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    if not os.path.exists(os.path.join(HERE, "encoder.cu")):
-        srcs.append("extractor_stub.cu")
     objs = []
     relink = force or not os.path.exists(OUT)
     for s in srcs:

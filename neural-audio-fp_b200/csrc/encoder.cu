@@ -8,9 +8,10 @@
 //                      layer's normalised fp16 activation: stride-2 axes are split into
 //                      (parity, half) dimensions of the tensor map, TF 'SAME' zero padding is TMA
 //                      out-of-bounds fill.  Persistent CTAs, 4-stage smem ring, fp32 accumulators
-//                      double-buffered in TMEM, 8 epilogue warps: bias + ELU + per-sample
-//                      sum / sum-of-squares (LayerNorm over (F,T,C)) + fp16 store.
-//   ln_apply_kernel    (y - mean) * rstd * gamma[f,t,c] + beta[f,t,c]  ->  fp16 operand of the next conv
+//                      double-buffered in TMEM, 16 epilogue warps: bias + ELU + per-sample
+//                      sum / sum-of-squares slots (LayerNorm over (F,T,C)) + fp16 store; the 128-channel
+//                      layers keep their weights resident in shared memory.
+//   ln_apply_kernel    reduces the slots, (y - mean) * rstd * gamma[f,t,c] + beta[f,t,c]  ->  fp16 operand of the next conv
 //   divenc_kernel      last LayerNorm + divide-and-encode head (128 x [8->32 ELU, 32->1]) + L2 norm.
 // fp16 operands / fp32 accumulation: measured against the fp64 oracle the fingerprints agree to
 // ~1e-4 (gate: cosine >= 0.9999, max abs <= 1e-3).
