@@ -125,9 +125,7 @@ __device__ __forceinline__ float elu(float v) {
 
 // ------------------------------------------------------------------------------------------
 // conv0_a: (B,256,32) fp32 log-mel -> (B,256,16,128) normalised fp16, stride 2 in time, pad (0,1).
-// K = 3: CUDA cores; fused with the log-mel max subtraction / clamp, bias, ELU and the LayerNorm
-// partial sums.  One warp per output position, lane owns 4 channels.  (A recompute variant --
-// statistics pass + apply pass, no pre-LN store -- measured slower: the ELU exponentials dominate.)
+// K = 3: CUDA cores; fused with the log-mel max subtraction / clamp, bias, ELU and the LayerNorm.
 // ------------------------------------------------------------------------------------------
 struct Conv0Lane {
     float w[3][4], bia[4];
@@ -142,13 +140,24 @@ __device__ __forceinline__ void conv0_load_lane(const float* __restrict__ w0, co
     const float4 v = reinterpret_cast<const float4*>(b0)[lane];
     L.bia[0] = v.x; L.bia[1] = v.y; L.bia[2] = v.z; L.bia[3] = v.w;
 }
-// Block (bx, seg): frequency rows 32 bx .. 32 bx + 31 of one segment; a warp takes rows warp, warp + 8, ...:
-// the row's 32 log-mel values are one coalesced load, the three taps of every output position come from
-// warp shuffles, and the 16 positions of the row are unrolled so that the stores use immediate offsets.
+// L1a never materialises its pre-LayerNorm output (1 MB fp16 per segment would make an HBM round trip):
+//   conv0_stats_kernel  ELU(conv) of every output, reduced to (sum, sum of squares) slots -- no store;
+//   conv0_ln_kernel     the same values recomputed, normalised with gamma/beta and stored once.
+// The exponentials are cheaper than the 2 GB of traffic they replace.
+// Both: a warp per frequency row; the row's 32 log-mel values are one coalesced load, the three taps of
+// every output position come from warp shuffles, the 16 positions of the row are unrolled; lane owns 4 channels.
+__device__ __forceinline__ void conv0_row(float v, const Conv0Lane& L, int tp, float (&o)[4]) {
+    const float x0 = __shfl_sync(0xffffffffu, v, 2 * tp);
+    const float x1 = __shfl_sync(0xffffffffu, v, 2 * tp + 1);
+    const float x2 = tp < 15 ? __shfl_sync(0xffffffffu, v, (2 * tp + 2) & 31) : 0.f;      // SAME padding (0, 1)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[c] = elu(L.bia[c] + x0 * L.w[0][c] + x1 * L.w[1][c] + x2 * L.w[2][c]);
+}
+
+// grid (8, n_seg): block (bx, seg) covers frequency rows 32 bx .. 32 bx + 31 of one segment
 __global__ void __launch_bounds__(256)
-conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int n_seg,
-             const float* __restrict__ w0, const float* __restrict__ b0, __half* __restrict__ y,
-             float* __restrict__ part) {
+conv0_stats_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int n_seg,
+                   const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ part) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.y;
     Conv0Lane L;
@@ -156,31 +165,21 @@ conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, in
     const bool raw = gmax != nullptr;
     const float sub = raw ? ord2f(gmax[seg / group_size]) : 0.f;
     const float* m = mel + static_cast<int64_t>(seg) * 8192;
-    __half* out = y + static_cast<int64_t>(seg) * (256 * 16 * 128);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         const int f = blockIdx.x * 32 + r * 8 + warp;
         float v = __ldg(m + f * 32 + lane);
         if (raw) v = fmaxf(v - sub, -80.f);                 // "- batch max, clamp -80" (melspectrogram.py:108-109)
-        uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(f) * (16 * 128)) + lane;
 #pragma unroll
         for (int tp = 0; tp < 16; ++tp) {
-            const float x0 = __shfl_sync(0xffffffffu, v, 2 * tp);
-            const float x1 = __shfl_sync(0xffffffffu, v, 2 * tp + 1);
-            const float x2 = tp < 15 ? __shfl_sync(0xffffffffu, v, (2 * tp + 2) & 31) : 0.f;      // SAME padding (0, 1)
             float o[4];
+            conv0_row(v, L, tp, o);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                o[c] = elu(L.bia[c] + x0 * L.w[0][c] + x1 * L.w[1][c] + x2 * L.w[2][c]);
                 s1 += o[c];
                 s2 += o[c] * o[c];
             }
-            __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            orow[tp * 32] = pk;
         }
     }
 #pragma unroll
@@ -188,8 +187,85 @@ conv0_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, in
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0)      // one slot per (segment, block, warp): summed in fixed order by ln_apply_kernel
+    if (lane == 0)      // one slot per (segment, block, warp): summed in fixed order by conv0_ln_kernel
         reinterpret_cast<float2*>(part)[static_cast<int64_t>(seg) * 64 + blockIdx.x * 8 + warp] = make_float2(s1, s2);
+}
+
+// grid (8, ceil(n_seg / 8)): block (bx, by) covers rows 32 bx .. 32 bx + 31 of segments 8 by .. 8 by + 7, so that
+// gamma / beta (8 B per element, shared by all segments) come from L1 after the first segment
+constexpr int CONV0_SEGS = 8;
+__global__ void __launch_bounds__(256)
+conv0_ln_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax, int64_t group_size, int n_seg,
+                const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ part,
+                float* __restrict__ stats_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __half* __restrict__ x) {
+    __shared__ float2 mr_s[CONV0_SEGS];          // (mean, rstd) of the block's segments
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg0 = blockIdx.y * CONV0_SEGS;
+    constexpr int PER_SEG = 256 * 16 * 128;
+    {
+        const int seg = seg0 + warp;             // 8 warps = CONV0_SEGS segments
+        if (seg < n_seg) {
+            const float2* p = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(seg) * 64;
+            double a = 0.0, b = 0.0;
+            for (int i = lane; i < 64; i += 32) {
+                const float2 v = p[i];
+                a += v.x;
+                b += v.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) {
+                const float inv_n = 1.f / static_cast<float>(PER_SEG);
+                const float s1 = static_cast<float>(a), s2 = static_cast<float>(b);
+                const float mean = s1 * inv_n;
+                const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+                mr_s[warp] = make_float2(mean, rsqrtf(var + LN_EPS));
+                if (blockIdx.x == 0 && stats_out) {
+                    stats_out[2 * seg] = s1;
+                    stats_out[2 * seg + 1] = s2;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    Conv0Lane L;
+    conv0_load_lane(w0, b0, lane, L);
+    const bool raw = gmax != nullptr;
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        const int f = blockIdx.x * 32 + r * 8 + warp;
+        const float4* g_row = reinterpret_cast<const float4*>(gamma + static_cast<int64_t>(f) * (16 * 128)) + lane;
+        const float4* b_row = reinterpret_cast<const float4*>(beta + static_cast<int64_t>(f) * (16 * 128)) + lane;
+#pragma unroll 1
+        for (int k = 0; k < CONV0_SEGS; ++k) {
+            const int seg = seg0 + k;
+            if (seg >= n_seg) break;
+            float v = __ldg(mel + static_cast<int64_t>(seg) * 8192 + f * 32 + lane);
+            if (raw) v = fmaxf(v - ord2f(gmax[seg / group_size]), -80.f);
+            const float mean = mr_s[k].x, rstd = mr_s[k].y;
+            uint2* orow = reinterpret_cast<uint2*>(x + static_cast<int64_t>(seg) * PER_SEG + static_cast<int64_t>(f) * (16 * 128)) + lane;
+#pragma unroll
+            for (int tp = 0; tp < 16; ++tp) {
+                float o[4];
+                conv0_row(v, L, tp, o);
+                // the normalisation sees the value as every other layer's does: rounded to fp16 once
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[c] = __half2float(__float2half_rn(o[c]));
+                const float4 g = __ldg(g_row + tp * 32), b = __ldg(b_row + tp * 32);
+                const float y0 = (o[0] - mean) * rstd * g.x + b.x, y1 = (o[1] - mean) * rstd * g.y + b.y;
+                const float y2 = (o[2] - mean) * rstd * g.z + b.z, y3 = (o[3] - mean) * rstd * g.w + b.w;
+                __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                orow[tp * 32] = pk;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -612,9 +688,9 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
         float* stats = s->stats + static_cast<size_t>(l) * ENC_CHUNK * 2;
         const int per = L.ms * L.c_out;
         if (l == 0) {
-            conv0_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, n, s->w0, s->bias[0], s->y, s->part);
-            ln_apply_kernel<<<dim3((per / 8 + 255) / 256, (n + LN_SEGS - 1) / LN_SEGS), 256, 0, st>>>(
-                s->y, s->part, 64, stats, s->ln_g[0], s->ln_b[0], s->x[0], per, n);
+            conv0_stats_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, n, s->w0, s->bias[0], s->part);
+            conv0_ln_kernel<<<dim3(8, (n + CONV0_SEGS - 1) / CONV0_SEGS), 256, 0, st>>>(
+                mel, gmax, group_size, n, s->w0, s->bias[0], s->part, stats, s->ln_g[0], s->ln_b[0], s->x[0]);
             ctx->launches += 2;
             continue;
         }
