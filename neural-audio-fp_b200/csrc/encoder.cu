@@ -43,12 +43,19 @@ struct ConvGeom {
     int tap_lo, tap_hi;                // taps that touch real data (others are all padding)
     int bt, bf, bb;                    // box extents in output positions: time, freq, segments
     int nt;                            // N tile
+    int ksplit;                        // 3 = this layer's input is stored [hi | hi | lo] per position and its
+                                       // weights [hi | lo | hi] per tap (hi + lo = the fp32 value to 2^-22):
+                                       // the same implicit GEMM then computes hi.hi + hi.lo + lo.hi
+    int osplit;                        // split factor of this layer's stored output (= ksplit of its consumer)
 };
+constexpr int ENC_SPLIT_FROM = 6;      // layers >= L4a: 25 % of the flops; removes ~35 % of the fingerprint's worst-case fp16 error
+constexpr int ENC_Y32_FROM = 6;        // the same layers store their pre-LayerNorm output in fp32 (<= 64 KB per segment)
 
 struct ConvParams {
     int m_total, ms, c_in, c_out, nt, n_ntiles, n_mtiles;
     int mode, pad_lo, tap_lo, tap_hi, kb_per_tap, tps, bf, bb;
     int groups;      // 32-row groups per segment (>= 1): slots of the LayerNorm partial sums
+    int y32;         // 1 = the pre-LayerNorm output is stored in fp32 (split-precision layers), 0 = fp16
 };
 
 struct EncoderState {
@@ -112,6 +119,8 @@ static void build_geometry(ConvGeom* g) {
             f = L.f_out; t = L.t_out; c = L.c_out;
         }
     }
+    for (int l = 0; l < 16; ++l) g[l].ksplit = l >= ENC_SPLIT_FROM ? 3 : 1;
+    for (int l = 0; l < 16; ++l) g[l].osplit = l + 1 < 16 ? g[l + 1].ksplit : 3;     // the head reads hi + lo too
 }
 
 // ELU(v) = v > 0 ? v : e^v - 1.  Only the v <= 0 side reaches the exponential, where e^v is in (0, 1]: the bare
@@ -252,9 +261,6 @@ conv0_ln_kernel(const float* __restrict__ mel, const int32_t* __restrict__ gmax,
             for (int tp = 0; tp < 16; ++tp) {
                 float o[4];
                 conv0_row(v, L, tp, o);
-                // the normalisation sees the value as every other layer's does: rounded to fp16 once
-#pragma unroll
-                for (int c = 0; c < 4; ++c) o[c] = __half2float(__float2half_rn(o[c]));
                 const float4 g = __ldg(g_row + tp * 32), b = __ldg(b_row + tp * 32);
                 const float y0 = (o[0] - mean) * rstd * g.x + b.x, y1 = (o[1] - mean) * rstd * g.y + b.y;
                 const float y2 = (o[2] - mean) * rstd * g.z + b.z, y3 = (o[3] - mean) * rstd * g.w + b.w;
@@ -430,6 +436,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld_32x32(taddr + c0, v);
                 tc_wait_ld();
                 uint32_t pk[16];
+                float ev[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     const float a = elu(__uint_as_float(v[j]) + bias_s[n_base + c0 + j]);
@@ -438,11 +445,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     s2 += a * a + b * b;
                     __half2 h = __floats2half2_rn(a, b);
                     pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                    ev[j] = a;
+                    ev[j + 1] = b;
                 }
-                if (row_ok) {
+                if (row_ok && !p.y32) {
                     uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                if (row_ok && p.y32) {        // same element offsets, 4-byte elements
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + static_cast<int64_t>(m) * p.c_out + n_base + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(ev[4 * j], ev[4 * j + 1], ev[4 * j + 2], ev[4 * j + 3]);
                 }
             }
             tc_fence_before();
@@ -479,7 +493,8 @@ static_assert(LN_SEGS == 8, "ln_apply_kernel maps its 8 warps to the block's seg
 // fixed order, double accumulation: bit-reproducible and no separate statistics launch.
 __global__ void __launch_bounds__(256)
 ln_apply_kernel(const __half* __restrict__ y, const float* __restrict__ part, int slots, float* __restrict__ stats_out,
-                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ x, int per_seg, int n_seg) {
+                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ x, int per_seg, int n_seg,
+                int c_out, int osplit, int y32) {
     __shared__ float2 mr_s[LN_SEGS];          // (mean, rstd) of the block's segments
     const int seg0 = blockIdx.y * LN_SEGS;
     {
@@ -524,19 +539,43 @@ ln_apply_kernel(const __half* __restrict__ y, const float* __restrict__ part, in
         if (b >= n_seg) break;
         const float mean = mr_s[k].x, rstd = mr_s[k].y;
         const int64_t idx = static_cast<int64_t>(b) * per_seg + off;
-        const uint4 raw = *reinterpret_cast<const uint4*>(y + idx);
-        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
-        uint4 outv;
+        float fv[8];
+        if (y32) {
+            const float4 r0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(y) + idx);
+            const float4 r1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(y) + idx + 4);
+            fv[0] = r0.x; fv[1] = r0.y; fv[2] = r0.z; fv[3] = r0.w; fv[4] = r1.x; fv[5] = r1.y; fv[6] = r1.z; fv[7] = r1.w;
+        } else {
+            const uint4 raw = *reinterpret_cast<const uint4*>(y + idx);
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hv[j]);
+                fv[2 * j] = f.x;
+                fv[2 * j + 1] = f.y;
+            }
+        }
+        uint4 outv, lowv;
         uint32_t* ov = reinterpret_cast<uint32_t*>(&outv);
+        uint32_t* lv = reinterpret_cast<uint32_t*>(&lowv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(hv[j]);
-            const float a = (f.x - mean) * rstd * gg[2 * j] + bb[2 * j];
-            const float c = (f.y - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1];
+            const float a = (fv[2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j];
+            const float c = (fv[2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1];
             __half2 h = __floats2half2_rn(a, c);
             ov[j] = *reinterpret_cast<uint32_t*>(&h);
+            const float2 back = __half22float2(h);
+            __half2 lo = __floats2half2_rn(a - back.x, c - back.y);
+            lv[j] = *reinterpret_cast<uint32_t*>(&lo);
         }
-        *reinterpret_cast<uint4*>(x + idx) = outv;
+        if (osplit == 1) {
+            *reinterpret_cast<uint4*>(x + idx) = outv;
+        } else {            // [hi | hi | lo] per position
+            const int pos = off / c_out, ch = off - pos * c_out;
+            __half* dst = x + (static_cast<int64_t>(b) * per_seg + static_cast<int64_t>(pos) * c_out) * 3 + ch;
+            *reinterpret_cast<uint4*>(dst) = outv;
+            *reinterpret_cast<uint4*>(dst + c_out) = outv;
+            *reinterpret_cast<uint4*>(dst + 2 * c_out) = lowv;
+        }
     }
 }
 
@@ -558,14 +597,17 @@ divenc_kernel(const __half* __restrict__ x, int n_seg, const float* __restrict__
     __syncthreads();
     const int seg = blockIdx.y * 128 + threadIdx.x;
     if (seg >= n_seg) return;
-    const uint4 rv = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(seg) * 1024 + q * 8);
+    // the last activation is stored [hi | hi | lo] (1024 channels each): hi + lo is the fp32 value to 2^-22
+    const uint4 rv = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(seg) * 3072 + q * 8);
+    const uint4 rl = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(seg) * 3072 + 2048 + q * 8);
     const __half2* hv = reinterpret_cast<const __half2*>(&rv);
+    const __half2* hl = reinterpret_cast<const __half2*>(&rl);
     float in[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hv[j]);
-        in[2 * j] = f.x;
-        in[2 * j + 1] = f.y;
+        const float2 f = __half22float2(hv[j]), g = __half22float2(hl[j]);
+        in[2 * j] = f.x + g.x;
+        in[2 * j + 1] = f.y + g.y;
     }
     float acc = b2[q];
 #pragma unroll 8
@@ -610,13 +652,14 @@ static int encoder_init(nafp_ctx* ctx) {
         const size_t per = static_cast<size_t>(L.ms) * L.c_out;
         if (per > ymax) ymax = per;
         // +128 rows of slack: the GEMM epilogue never writes past m_total, TMA boxes may read past it
-        NAFP_CUDA(cudaMalloc(&s->x[l], (static_cast<size_t>(ENC_CHUNK) * per + 128 * L.c_out) * sizeof(__half)));
-        NAFP_CUDA(cudaMemset(s->x[l], 0, (static_cast<size_t>(ENC_CHUNK) * per + 128 * L.c_out) * sizeof(__half)));
+        const size_t x_elems = (static_cast<size_t>(ENC_CHUNK) * per + 128 * L.c_out) * L.osplit;
+        NAFP_CUDA(cudaMalloc(&s->x[l], x_elems * sizeof(__half)));
+        NAFP_CUDA(cudaMemset(s->x[l], 0, x_elems * sizeof(__half)));
         NAFP_CUDA(cudaMalloc(&s->bias[l], L.c_out * sizeof(float)));
         NAFP_CUDA(cudaMalloc(&s->ln_g[l], per * sizeof(float)));
         NAFP_CUDA(cudaMalloc(&s->ln_b[l], per * sizeof(float)));
         if (l == 0) NAFP_CUDA(cudaMalloc(&s->w0, 3 * 128 * sizeof(float)));
-        else NAFP_CUDA(cudaMalloc(&s->wt[l], static_cast<size_t>(L.c_out) * 3 * L.c_in * sizeof(__half)));
+        else NAFP_CUDA(cudaMalloc(&s->wt[l], static_cast<size_t>(L.c_out) * 3 * L.c_in * L.ksplit * sizeof(__half)));
     }
     NAFP_CUDA(cudaMalloc(&s->y, (static_cast<size_t>(ENC_CHUNK) * ymax + 128 * 1024) * sizeof(__half)));
     NAFP_CUDA(cudaMalloc(&s->stats, static_cast<size_t>(ENC_LAYERS) * ENC_CHUNK * 2 * sizeof(float)));
@@ -632,7 +675,7 @@ static int encoder_init(nafp_ctx* ctx) {
     // tensor maps (activation maps are sized for ENC_CHUNK segments; rows past the live batch are masked)
     for (int l = 1; l < ENC_LAYERS; ++l) {
         const ConvGeom& L = s->g[l];
-        const uint64_t C = L.c_in, T = L.t_in, F = L.f_in, B = ENC_CHUNK;
+        const uint64_t C = static_cast<uint64_t>(L.c_in) * L.ksplit, T = L.t_in, F = L.f_in, B = ENC_CHUNK;
         uint64_t dims[5], str[5];
         uint32_t box[5];
         int rank;
@@ -695,17 +738,18 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
             continue;
         }
         ConvParams p;
-        p.m_total = n * L.ms; p.ms = L.ms; p.c_in = L.c_in; p.c_out = L.c_out; p.nt = L.nt;
+        p.m_total = n * L.ms; p.ms = L.ms; p.c_in = L.c_in * L.ksplit; p.c_out = L.c_out; p.nt = L.nt;
         p.n_ntiles = L.c_out / L.nt; p.n_mtiles = (p.m_total + 127) / 128;
         p.mode = L.mode; p.pad_lo = L.pad_lo; p.tap_lo = L.tap_lo; p.tap_hi = L.tap_hi;
-        p.kb_per_tap = L.c_in / 64; p.tps = L.ms >= 128 ? L.ms / 128 : 0; p.bf = L.bf; p.bb = L.bb;
+        p.kb_per_tap = L.c_in * L.ksplit / 64; p.tps = L.ms >= 128 ? L.ms / 128 : 0; p.bf = L.bf; p.bb = L.bb;
         p.groups = L.ms >= 32 ? L.ms / 32 : 1;
+        p.y32 = l >= ENC_Y32_FROM ? 1 : 0;      // small layers keep their pre-LN output in fp32 (one fp16 rounding less)
         const int slots = p.groups * p.n_ntiles * CONV_EPI_PARTS;
         const int tiles = p.n_mtiles * p.n_ntiles;
         const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
         conv_gemm_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(s->tmA[l], s->tmB[l], p, s->bias[l], s->y, s->part);
         ln_apply_kernel<<<dim3((per / 8 + 255) / 256, (n + LN_SEGS - 1) / LN_SEGS), 256, 0, st>>>(
-            s->y, s->part, slots, stats, s->ln_g[l], s->ln_b[l], s->x[l], per, n);
+            s->y, s->part, slots, stats, s->ln_g[l], s->ln_b[l], s->x[l], per, n, L.c_out, L.osplit, p.y32);
         ctx->launches += 2;
     }
     divenc_kernel<<<dim3(EMB, (n + 127) / 128), 128, 0, st>>>(s->x[ENC_LAYERS - 1], n, s->dw1, s->db1, s->dw2, s->db2, s->raw);
@@ -760,13 +804,21 @@ int nafp_weights_load(nafp_ctx* ctx, const float* const* conv_w, const float* co
             NAFP_CUDA(cudaMemcpy(s->w0, conv_w[0], 3 * 128 * sizeof(float), cudaMemcpyHostToDevice));
         } else {
             // HWIO [tap][cin][cout] -> K-major B operand [cout][tap*cin + cin] in fp16
-            const int K = 3 * L.c_in;
+            // split layers: per tap [hi | lo | hi], matching the [hi | hi | lo] activations
+            const int ce = L.c_in * L.ksplit, K = 3 * ce;
             std::vector<__half> wt(static_cast<size_t>(L.c_out) * K);
             for (int tap = 0; tap < 3; ++tap)
                 for (int ci = 0; ci < L.c_in; ++ci) {
                     const float* src = conv_w[l] + (static_cast<size_t>(tap) * L.c_in + ci) * L.c_out;
-                    for (int co = 0; co < L.c_out; ++co)
-                        wt[static_cast<size_t>(co) * K + tap * L.c_in + ci] = __float2half_rn(src[co]);
+                    for (int co = 0; co < L.c_out; ++co) {
+                        const __half hi = __float2half_rn(src[co]);
+                        __half* row = &wt[static_cast<size_t>(co) * K + tap * ce];
+                        row[ci] = hi;
+                        if (L.ksplit == 3) {
+                            row[L.c_in + ci] = __float2half_rn(src[co] - __half2float(hi));
+                            row[2 * L.c_in + ci] = hi;
+                        }
+                    }
                 }
             NAFP_CUDA(cudaMemcpy(s->wt[l], wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
         }
@@ -839,10 +891,18 @@ int nafp_encoder_activation_host(nafp_ctx* ctx, int layer, int64_t n_seg, float*
                  (long long)s->last_n);
     const ConvGeom& L = s->g[layer];
     const size_t n = static_cast<size_t>(n_seg) * L.ms * L.c_out;
-    std::vector<__half> tmp(n);
+    std::vector<__half> tmp(n * L.osplit);
     NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
-    NAFP_CUDA(cudaMemcpy(tmp.data(), s->x[layer], n * sizeof(__half), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) out_host[i] = __half2float(tmp[i]);
+    NAFP_CUDA(cudaMemcpy(tmp.data(), s->x[layer], tmp.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+    if (L.osplit == 1) {
+        for (size_t i = 0; i < n; ++i) out_host[i] = __half2float(tmp[i]);
+    } else {                // [hi | hi | lo] per position
+        const size_t C = L.c_out;
+        for (size_t i = 0; i < n; ++i) {
+            const size_t pos = i / C, c = i % C;
+            out_host[i] = __half2float(tmp[pos * 3 * C + c]) + __half2float(tmp[pos * 3 * C + 2 * C + c]);
+        }
+    }
     return NAFP_OK;
 }
 
