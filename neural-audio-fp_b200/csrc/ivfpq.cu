@@ -27,7 +27,7 @@ namespace nafp {
 constexpr int PQ_MAX_M = 64;
 constexpr int PQ_KSUB = 256;
 constexpr int IVF_MAX_NLIST = 1024;
-constexpr int IVF_SCAN_CAP = 1024;        // candidate buffer per (query, list) CTA
+constexpr int IVF_SCAN_CAP = 512;         // candidate buffer per (query, list) CTA: two 512-key sorts per list instead of two 1024-key ones
 
 struct IvfPq {
     int nlist = 256, m = 64, dsub = 2;
