@@ -10,7 +10,10 @@
 //           ivfpq_scan_kernel  (one CTA per (query row, probed list): 64 x 256 fp32 look-up table in
 //                               shared memory, ADC scan of the list's codes, block top-k) ->
 //           topk merge of the nprobe partial lists.
-// HBM-bound: 0.156 * N * 68 bytes per query row at nprobe / nlist = 40 / 256.
+//           -- that is the reference formulation and the fallback.  The fast path uses the identity
+//           ADC(q, code) = |q - xhat|^2 (xhat = the row's reconstruction): a flat index over xhat (same row
+//           order) is searched with the tensor-core scan for the 64 nearest reconstructions, the candidates
+//           outside the nprobe nearest lists are dropped, and k survivors in order ARE the IVF-PQ answer.
 #include <algorithm>
 #include <cfloat>
 #include <climits>
@@ -49,7 +52,26 @@ struct IvfPq {
     int64_t* partI = nullptr;
     int64_t scratch_nq = 0;
     int scratch_nprobe = 0, scratch_k = 0;
+    // reconstruction path: ADC(q, code) = |q - xhat|^2 with xhat = coarse[list] + pq[m][code_m], so the IVF-PQ
+    // answer is the EXACT nearest-neighbour search over the reconstructed rows restricted to the probed
+    // lists.  B200 has the HBM to keep xhat resident: a flat index over it lets the tensor-core scan replace
+    // nq * nprobe * |list| * M shared-memory LUT gathers; the LUT kernel answers what the filter cannot prove.
+    nafp_index* recon = nullptr;  // flat index over xhat, same row order
+    float* xhat_tmp = nullptr;    // [RECON_CHUNK][128] decode staging
+    float* candD = nullptr;       // [nq_cap][RECON_K]
+    int64_t* candI = nullptr;
+    int64_t cand_nq = 0;
+    int32_t* probes_all = nullptr;    // [nq][nprobe] of the whole call
+    int64_t probes_all_elems = 0;
+    int32_t* redo_rows = nullptr; // query rows the filter could not answer, + counter at [cap]
+    float* redo_q = nullptr;      // gathered copies of those rows, and their results
+    float* redo_D = nullptr;
+    int64_t* redo_I = nullptr;
+    int64_t redo_cap = 0;
+    unsigned long long lut_rows = 0;      // rows answered by the LUT kernel since creation (statistics)
 };
+constexpr int RECON_K = 64;               // candidates fetched from the flat scan per query row
+constexpr int64_t RECON_CHUNK = 1 << 20;  // rows decoded per add step
 
 // ------------------------------------------------------------------------------------------ k-means
 // nearest centroid of `dim`-dimensional points (row stride `ld` floats); one warp per point, lane l
@@ -413,6 +435,79 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
     }
 }
 
+// xhat[row] = coarse[assign[row]] + concat_m pq[m][code[row][m]]; one warp per row, lane owns 4 dims
+__global__ void ivfpq_decode_kernel(const int32_t* __restrict__ assign, const uint8_t* __restrict__ codes, int64_t row0, int64_t n,
+                                    const float* __restrict__ coarse, const float* __restrict__ pq, int m, int dsub,
+                                    float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int64_t row = row0 + r;
+    const int l = assign[row];
+    float4 v = reinterpret_cast<const float4*>(coarse + static_cast<int64_t>(l) * D128)[lane];
+    float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int d = 4 * lane + j, sub = d / dsub, w = d - sub * dsub;
+        vv[j] += pq[(static_cast<int64_t>(sub) * PQ_KSUB + codes[row * m + sub]) * dsub + w];
+    }
+    reinterpret_cast<float4*>(out + r * D128)[lane] = v;
+}
+
+// One warp per query row: keep the flat scan's candidates whose list is probed, in order.  k of them (or all
+// stored rows of the probed lists) ARE the restricted top-k; otherwise the row goes to the LUT kernel.
+__global__ void ivfpq_filter_kernel(const float* __restrict__ candD, const int64_t* __restrict__ candI, int64_t nq, int k,
+                                    const int32_t* __restrict__ probes, int nprobe, const int32_t* __restrict__ assign,
+                                    int64_t label_offset, float* __restrict__ D, int64_t* __restrict__ I,
+                                    int32_t* __restrict__ redo_rows, int32_t* __restrict__ redo_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    int kept = 0;
+    bool exhausted = false;            // fewer than RECON_K rows exist at all: the candidate list is complete
+    for (int c0 = 0; c0 < RECON_K && kept < k; c0 += 32) {
+        const int c = c0 + lane;
+        const int64_t id = candI[q * RECON_K + c];
+        bool in = false;
+        if (id >= 0) {
+            const int l = assign[id];
+            for (int p = 0; p < nprobe; ++p) in = in || (probes[q * nprobe + p] == l);
+        }
+        if (__any_sync(0xffffffffu, id < 0)) exhausted = true;
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        const int pos = kept + __popc(mask & ((1u << lane) - 1));
+        if (in && pos < k) {
+            D[q * k + pos] = candD[q * RECON_K + c];
+            I[q * k + pos] = id + label_offset;
+        }
+        kept += __popc(mask);
+    }
+    if (kept >= k) return;
+    if (exhausted) {                   // everything that exists was looked at: pad like faiss
+        for (int j = kept + lane; j < k; j += 32) {
+            D[q * k + j] = INFINITY;
+            I[q * k + j] = -1;
+        }
+        return;
+    }
+    if (lane == 0) redo_rows[atomicAdd(redo_count, 1)] = static_cast<int32_t>(q);
+}
+
+__global__ void ivfpq_gather_q_kernel(const float* __restrict__ q, const int32_t* __restrict__ rows, int64_t n, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    reinterpret_cast<float4*>(out + w * D128)[lane] = reinterpret_cast<const float4*>(q + static_cast<int64_t>(rows[w]) * D128)[lane];
+}
+__global__ void ivfpq_scatter_kernel(const float* __restrict__ Ds, const int64_t* __restrict__ Is, const int32_t* __restrict__ rows,
+                                     int64_t n, int k, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n * k) return;
+    const int64_t w = i / k, j = i - w * k;
+    D[static_cast<int64_t>(rows[w]) * k + j] = Ds[i];
+    I[static_cast<int64_t>(rows[w]) * k + j] = Is[i];
+}
+
 // ------------------------------------------------------------------------------------------ host
 int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits) {
     NAFP_REQUIRE(nbits == 8, NAFP_ERR_UNSUPPORTED, "ivfpq: nbits=%d (only 8, as in the reference)", nbits);
@@ -426,14 +521,18 @@ int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits) {
     NAFP_CUDA(cudaMalloc(&s->coarse, static_cast<size_t>(nlist) * D128 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->pq, static_cast<size_t>(m) * PQ_KSUB * s->dsub * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->loff, (nlist + 1) * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&s->xhat_tmp, static_cast<size_t>(RECON_CHUNK) * D128 * sizeof(float)));
     idx->ivf = s;
+    NAFP_TRY(nafp_index_create(idx->ctx, NAFP_INDEX_FLAT_L2, D128, 0, 0, 8, &s->recon));
     return NAFP_OK;
 }
 
 void ivfpq_destroy(nafp_index* idx) {
     IvfPq* s = idx->ivf;
     if (!s) return;
-    void* bufs[] = {s->coarse, s->pq, s->assign, s->codes, s->lcodes, s->lids, s->loff, s->probes, s->partD, s->partI};
+    if (s->recon) nafp_index_destroy(s->recon);
+    void* bufs[] = {s->coarse, s->pq, s->assign, s->codes, s->lcodes, s->lids, s->loff, s->probes, s->partD, s->partI,
+                    s->xhat_tmp, s->candD, s->candI, s->probes_all, s->redo_rows, s->redo_q, s->redo_D, s->redo_I};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     idx->ivf = nullptr;
@@ -510,6 +609,14 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
     ctx->launches++;
     NAFP_CUDA(cudaGetLastError());
     s->dirty = true;
+    NAFP_TRY(index_reserve(s->recon, idx->cap));
+    for (int64_t r0 = 0; r0 < n; r0 += RECON_CHUNK) {
+        const int64_t nc = n - r0 < RECON_CHUNK ? n - r0 : RECON_CHUNK;
+        ivfpq_decode_kernel<<<static_cast<unsigned>((nc * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            s->assign, s->codes, row0 + r0, nc, s->coarse, s->pq, s->m, s->dsub, s->xhat_tmp);
+        ctx->launches++;
+        NAFP_TRY(flat_add_dev(s->recon, s->xhat_tmp, nc, false));
+    }
     return NAFP_OK;
 }
 
@@ -563,11 +670,10 @@ static int build_lists(nafp_index* idx) {
 __global__ void topk_merge_kernel(const float* __restrict__ D_all, const int64_t* __restrict__ I_all, int W, int64_t nq,
                                   int k, float* __restrict__ D_out, int64_t* __restrict__ I_out);
 
-int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+// the reference formulation: per (query row, probed list) LUT + ADC scan of the list's codes
+static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
     IvfPq* s = idx->ivf;
     nafp_ctx* ctx = idx->ctx;
-    NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "ivfpq search: index is not trained");
-    NAFP_CUDA(cudaSetDevice(ctx->device));
     if (nq == 0) return NAFP_OK;
     const int nprobe = idx->nprobe < s->nlist ? idx->nprobe : s->nlist;
     NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
@@ -601,7 +707,74 @@ int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, flo
         ctx->launches += 3;
     }
     NAFP_CUDA(cudaGetLastError());
+    s->lut_rows += static_cast<unsigned long long>(nq);
+    return NAFP_OK;
+}
+
+int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    IvfPq* s = idx->ivf;
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "ivfpq search: index is not trained");
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    if (nq == 0) return NAFP_OK;
+    const int nprobe = idx->nprobe < s->nlist ? idx->nprobe : s->nlist;
+    NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
+                 "ivfpq search: need k <= %d and nprobe*k <= 2048 (nprobe %d, k %d)", MAX_K, nprobe, k);
     idx->host_rows += nq;
+    if (k > RECON_K / 2 || nq >= (1ll << 31)) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
+
+    // 1. exact top-RECON_K over the reconstructed rows (tensor-core scan + fp32 re-rank)
+    if (s->cand_nq < nq) {
+        if (s->candD) cudaFree(s->candD);
+        if (s->candI) cudaFree(s->candI);
+        s->candD = nullptr; s->candI = nullptr; s->cand_nq = 0;
+        NAFP_CUDA(cudaMalloc(&s->candD, static_cast<size_t>(nq) * RECON_K * sizeof(float)));
+        NAFP_CUDA(cudaMalloc(&s->candI, static_cast<size_t>(nq) * RECON_K * sizeof(int64_t)));
+        s->cand_nq = nq;
+    }
+    if (s->probes_all_elems < nq * nprobe) {
+        if (s->probes_all) cudaFree(s->probes_all);
+        s->probes_all = nullptr; s->probes_all_elems = 0;
+        NAFP_CUDA(cudaMalloc(&s->probes_all, static_cast<size_t>(nq) * nprobe * sizeof(int32_t)));
+        s->probes_all_elems = nq * nprobe;
+    }
+    int32_t* probes_all = s->probes_all;
+    if (s->redo_cap < nq) {
+        void* old[] = {s->redo_rows, s->redo_q, s->redo_D, s->redo_I};
+        for (void* b : old) if (b) cudaFree(b);
+        s->redo_rows = nullptr; s->redo_q = nullptr; s->redo_D = nullptr; s->redo_I = nullptr; s->redo_cap = 0;
+        NAFP_CUDA(cudaMalloc(&s->redo_rows, static_cast<size_t>(nq + 1) * sizeof(int32_t)));
+        s->redo_cap = nq;
+    }
+    int32_t* redo_count = s->redo_rows + s->redo_cap;
+    NAFP_CUDA(cudaMemsetAsync(redo_count, 0, sizeof(int32_t), ctx->stream));
+    s->recon->search_rows = idx->search_rows;
+    NAFP_TRY(flat_search_dev(s->recon, q_dev, nq, RECON_K, s->candD, s->candI));
+    // 2. the nprobe nearest lists of every row, 3. keep the candidates that live in them
+    ivfpq_probe_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, 0, ctx->stream>>>(q_dev, nq, s->coarse, s->nlist, nprobe, probes_all);
+    ivfpq_filter_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, 0, ctx->stream>>>(s->candD, s->candI, nq, k, probes_all, nprobe,
+                                                                                     s->assign, idx->label_offset, D_dev, I_dev,
+                                                                                     s->redo_rows, redo_count);
+    ctx->launches += 2;
+    NAFP_CUDA(cudaGetLastError());
+    int32_t n_redo = 0;
+    NAFP_CUDA(cudaMemcpyAsync(&n_redo, redo_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    // 4. rows with fewer than k probed rows among their RECON_K nearest: the LUT scan of their lists
+    if (n_redo > 0) {
+        if (!s->redo_q) {
+            NAFP_CUDA(cudaMalloc(&s->redo_q, static_cast<size_t>(s->redo_cap) * D128 * sizeof(float)));
+            NAFP_CUDA(cudaMalloc(&s->redo_D, static_cast<size_t>(s->redo_cap) * MAX_K * sizeof(float)));
+            NAFP_CUDA(cudaMalloc(&s->redo_I, static_cast<size_t>(s->redo_cap) * MAX_K * sizeof(int64_t)));
+        }
+        ivfpq_gather_q_kernel<<<static_cast<unsigned>((static_cast<int64_t>(n_redo) * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            q_dev, s->redo_rows, n_redo, s->redo_q);
+        NAFP_TRY(ivfpq_search_lut(idx, s->redo_q, n_redo, k, s->redo_D, s->redo_I));
+        ivfpq_scatter_kernel<<<static_cast<unsigned>((static_cast<int64_t>(n_redo) * k + 255) / 256), 256, 0, ctx->stream>>>(
+            s->redo_D, s->redo_I, s->redo_rows, n_redo, k, D_dev, I_dev);
+        ctx->launches += 2;
+        NAFP_CUDA(cudaGetLastError());
+    }
     return NAFP_OK;
 }
 
