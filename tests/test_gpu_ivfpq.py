@@ -46,6 +46,36 @@ def test_ivfpq_same_quantizers_matches_oracle():
     assert np.abs(top1_g - top1_o).max() <= 100.0 / len(ids) + 1e-9
 
 
+@pytest.mark.parametrize("nprobe,k", [(1, 20), (3, 5), (40, 40)])
+def test_ivfpq_fallback_and_fast_path_agree_with_oracle(nprobe, k):
+    """Few probed lists (most rows lack k probed rows among their 64 nearest reconstructions -> LUT kernel),
+    or k above the fast path's limit: same answers as the oracle with the same quantizers."""
+    from nafp_b200 import synth
+    from nafp_b200.eval.utils.get_index import IVFPQ, Index
+    from oracle.ivfpq_index import IVFPQ as OracleIVFPQ
+    dummy, db, query = synth.synth_search_set(12000, 590, seed=17)
+    g = Index(IVFPQ, 128, nlist=256, pq_m=64, pq_nbits=8)
+    g.train(dummy, seed=7)
+    g.add(dummy)
+    g.add(db)
+    g.nprobe = nprobe
+    o = OracleIVFPQ(128, 256, 64, 8)
+    o.set_params(*g.ivfpq_params())
+    o.add(dummy)
+    o.add(db)
+    o.nprobe = nprobe
+    q = query[:48]
+    Dg, Ig = g.search(q, k)
+    Do, Io = o.search(q, k)
+    fin = np.isfinite(Do)
+    assert (np.isfinite(Dg) == fin).all() and ((Ig < 0) == (Io < 0)).all()
+    np.testing.assert_allclose(Dg[fin], Do[fin], rtol=0, atol=2e-5)
+    same = Ig == Io
+    assert same.mean() >= 0.98
+    for r, c in np.argwhere(~same):            # only permutations among (near-)equal ADC distances
+        assert Ig[r, c] in Io[r] or abs(Dg[r, c] - Do[r, min(c + 1, k - 1)]) < 2e-5 or abs(Dg[r, c] - Do[r, c]) < 2e-5
+
+
 def test_ivfpq_training_quality_and_hit_rate():
     """Own k-means on the GPU vs the oracle's own k-means: quantisation error and top-1 recall agree."""
     from nafp_b200 import synth
