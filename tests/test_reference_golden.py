@@ -69,3 +69,21 @@ def test_product_cli_reproduces_reference_eval_loop(tmp_path, ref_eval):
     run_eval(emb, None, 'l2', False, 1e7, ids_path, gold.EVAL["seq_lens"], gold.EVAL["k_probe"], 5)
     np.testing.assert_array_equal(np.load(emb + "raw_score.npy"), ref_eval["raw_score"])
     np.testing.assert_array_equal(np.load(emb + "test_ids.npy"), ref_eval["test_ids"])
+
+
+@pytest.mark.gpu
+def test_product_cli_ivfpq_runs_the_same_job(tmp_path, ref_eval):
+    """index_type 'ivfpq' through the evaluate entry point (train on dummy_db, nprobe 40): same outputs, and the
+    approximate index loses little against the reference loop's exact-search hit rates on this fixture."""
+    from nafp_b200.eval.eval_search import run_eval
+    emb = str(tmp_path) + "/"
+    gold.write_emb_dir(emb)
+    ids_path = os.path.join(emb, "ids.npy")
+    np.save(ids_path, np.asarray(gold.EVAL["test_ids"], np.int64))
+    run_eval(emb, None, 'ivfpq', False, 1e7, ids_path, gold.EVAL["seq_lens"], gold.EVAL["k_probe"], 5)
+    raw = np.load(emb + "raw_score.npy")
+    assert raw.shape == ref_eval["raw_score"].shape
+    np.testing.assert_array_equal(np.load(emb + "test_ids.npy"), ref_eval["test_ids"])
+    top1, top1_flat = 100.0 * raw[:, :6].mean(0), 100.0 * ref_eval["raw_score"][:, :6].mean(0)
+    assert (top1 <= top1_flat + 3.0).all() and (top1 >= top1_flat - 20.0).all(), (top1, top1_flat)
+    assert top1[-1] >= 97.0
