@@ -398,7 +398,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t row0 = static_cast<uint32_t>(cta) * SCAN_TILE + part * PART_COLS;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
-                mbar_wait(&bars->tfull[acc], (uc >> 1) & 1);
+                mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
                 tc_fence_after();
                 float munit = NEG_INF;
 #pragma unroll 1
@@ -445,7 +445,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             bool end = false;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
-                mbar_wait(&bars->tfull[acc], (uc >> 1) & 1);
+                mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
                 if (hq == 0) {
                     const int tile = smem_ld_volatile(&bars->tile_of[i & 7]);
                     if (tile < 0) {
