@@ -30,7 +30,9 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
                bool finish, const int32_t** gmax_out);
 
 constexpr int ENC_LAYERS = 16;
-constexpr int ENC_CHUNK = 1000;        // segments per encoder pass (activation buffers are sized for this)
+constexpr int ENC_CHUNK_MAX = 4000;    // most segments of one encoder pass (2.3 MB of activations each): at 1,000 the
+                                       // six last layers have fewer tiles than the chip has SMs
+constexpr int ENC_CHUNK_MIN = 1000;    // the activation arena starts here and grows on demand (encoder_reserve)
 constexpr int EMB = 128;
 constexpr float LN_EPS = 1e-3f;        // Keras LayerNormalization default
 constexpr float L2_EPS = 1e-12f;       // tf.math.l2_normalize default
@@ -68,12 +70,16 @@ struct EncoderState {
     float *dw1 = nullptr, *db1 = nullptr, *dw2 = nullptr, *db2 = nullptr;
     __half* y = nullptr;                       // pre-LayerNorm scratch, largest layer
     __half* x[ENC_LAYERS] = {};                // normalised activations
-    float* stats = nullptr;                    // [ENC_LAYERS][ENC_CHUNK][2]
-    float* part = nullptr;                     // [ENC_CHUNK][128][2] partial LayerNorm sums of the running layer
-    float* mel = nullptr;                      // (ENC_CHUNK, 256, 32) for the fused entry points
-    void* xin = nullptr;                       // (ENC_CHUNK, 8000) staging for the *_host entry points
-    float* emb = nullptr;                      // (ENC_CHUNK, 128)
-    float* raw = nullptr;                      // (ENC_CHUNK, 128) head outputs before the L2 normalisation
+    int cap = 0;                               // segments the arena below holds (ENC_CHUNK_MIN .. ENC_CHUNK_MAX)
+    float* stats = nullptr;                    // [ENC_LAYERS][cap][2]
+    float* part = nullptr;                     // [cap][64 x parts][2] partial LayerNorm sums of the running layer
+    float* mel = nullptr;                      // (cap, 256, 32) for the fused entry points
+    void* xin[2] = {nullptr, nullptr};         // (cap, 8000) staging for the *_host entry points, double-buffered:
+    cudaStream_t copy_stream = nullptr;        // the upload of pass i+1 runs on copy_stream under the kernels of pass i
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}; // xin[b] has landed
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};   // the last pass that read xin[b] has finished
+    float* emb = nullptr;                      // (cap, 128)
+    float* raw = nullptr;                      // (cap, 128) head outputs before the L2 normalisation
     CUtensorMap tmA[ENC_LAYERS], tmB[ENC_LAYERS];
     bool weights = false;
     int64_t last_n = 0;                        // segments of the last pass (activation probe)
@@ -646,36 +652,86 @@ static int encoder_init(nafp_ctx* ctx) {
     if (ctx->encoder) return NAFP_OK;
     EncoderState* s = new EncoderState();
     build_geometry(s->g);
-    size_t ymax = 0;
     for (int l = 0; l < ENC_LAYERS; ++l) {
         const ConvGeom& L = s->g[l];
         const size_t per = static_cast<size_t>(L.ms) * L.c_out;
-        if (per > ymax) ymax = per;
-        // +128 rows of slack: the GEMM epilogue never writes past m_total, TMA boxes may read past it
-        const size_t x_elems = (static_cast<size_t>(ENC_CHUNK) * per + 128 * L.c_out) * L.osplit;
-        NAFP_CUDA(cudaMalloc(&s->x[l], x_elems * sizeof(__half)));
-        NAFP_CUDA(cudaMemset(s->x[l], 0, x_elems * sizeof(__half)));
         NAFP_CUDA(cudaMalloc(&s->bias[l], L.c_out * sizeof(float)));
         NAFP_CUDA(cudaMalloc(&s->ln_g[l], per * sizeof(float)));
         NAFP_CUDA(cudaMalloc(&s->ln_b[l], per * sizeof(float)));
         if (l == 0) NAFP_CUDA(cudaMalloc(&s->w0, 3 * 128 * sizeof(float)));
         else NAFP_CUDA(cudaMalloc(&s->wt[l], static_cast<size_t>(L.c_out) * 3 * L.c_in * L.ksplit * sizeof(__half)));
     }
-    NAFP_CUDA(cudaMalloc(&s->y, (static_cast<size_t>(ENC_CHUNK) * ymax + 128 * 1024) * sizeof(__half)));
-    NAFP_CUDA(cudaMalloc(&s->stats, static_cast<size_t>(ENC_LAYERS) * ENC_CHUNK * 2 * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&s->part, static_cast<size_t>(ENC_CHUNK) * 64 * CONV_EPI_PARTS * 2 * sizeof(float)));   // <= 64 row groups x parts float2 slots per segment
     NAFP_CUDA(cudaMalloc(&s->dw1, 128 * 8 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->db1, 128 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->dw2, 128 * 32 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->db2, 128 * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&s->mel, static_cast<size_t>(ENC_CHUNK) * 8192 * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&s->xin, static_cast<size_t>(ENC_CHUNK) * 8000 * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&s->emb, static_cast<size_t>(ENC_CHUNK) * EMB * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&s->raw, static_cast<size_t>(ENC_CHUNK) * EMB * sizeof(float)));
-    // tensor maps (activation maps are sized for ENC_CHUNK segments; rows past the live batch are masked)
     for (int l = 1; l < ENC_LAYERS; ++l) {
         const ConvGeom& L = s->g[l];
-        const uint64_t C = static_cast<uint64_t>(L.c_in) * L.ksplit, T = L.t_in, F = L.f_in, B = ENC_CHUNK;
+        const uint64_t C = static_cast<uint64_t>(L.c_in) * L.ksplit;
+        const uint64_t wd[2] = {3 * C, static_cast<uint64_t>(L.c_out)};
+        const uint64_t ws[2] = {2, 3 * C * 2};
+        const uint32_t wb[2] = {64, static_cast<uint32_t>(L.nt)};
+        NAFP_TRY(make_tensor_map(&s->tmB[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, s->wt[l], wd, ws, wb, nullptr,
+                                 CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+    NAFP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    NAFP_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        NAFP_CUDA(cudaEventCreateWithFlags(&s->ev_up[b], cudaEventDisableTiming));
+        NAFP_CUDA(cudaEventCreateWithFlags(&s->ev_free[b], cudaEventDisableTiming));
+    }
+    ctx->encoder = s;
+    return NAFP_OK;
+}
+
+static void encoder_release_arena(EncoderState* s) {
+    for (int l = 0; l < ENC_LAYERS; ++l) {
+        if (s->x[l]) cudaFree(s->x[l]);
+        s->x[l] = nullptr;
+    }
+    void** bufs[] = {reinterpret_cast<void**>(&s->y), reinterpret_cast<void**>(&s->stats), reinterpret_cast<void**>(&s->part),
+                     reinterpret_cast<void**>(&s->raw), reinterpret_cast<void**>(&s->mel), &s->xin[0], &s->xin[1],
+                     reinterpret_cast<void**>(&s->emb)};
+    for (void** b : bufs) {
+        if (*b) cudaFree(*b);
+        *b = nullptr;
+    }
+    s->cap = 0;
+    s->last_n = 0;
+}
+
+// The activation arena (2.3 MB per segment) and the activation tensor maps are sized for `cap` segments; a pass of
+// more segments than that re-allocates them (ENC_CHUNK_MIN, then the request rounded up to 1,000, <= ENC_CHUNK_MAX).
+static int encoder_reserve(nafp_ctx* ctx, int64_t n) {
+    EncoderState* s = ctx->encoder;
+    if (n <= s->cap) return NAFP_OK;
+    int64_t cap = (n + 999) / 1000 * 1000;
+    if (cap < ENC_CHUNK_MIN) cap = ENC_CHUNK_MIN;
+    if (cap > ENC_CHUNK_MAX) cap = ENC_CHUNK_MAX;
+    NAFP_REQUIRE(n <= cap, NAFP_ERR_INVALID, "encoder: %lld segments in one pass (at most %d)", (long long)n, ENC_CHUNK_MAX);
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    encoder_release_arena(s);
+    size_t ymax = 0;
+    for (int l = 0; l < ENC_LAYERS; ++l) {
+        const ConvGeom& L = s->g[l];
+        const size_t per = static_cast<size_t>(L.ms) * L.c_out;
+        if (per > ymax) ymax = per;
+        // +128 rows of slack: the GEMM epilogue never writes past m_total, TMA boxes may read past it
+        const size_t x_elems = (static_cast<size_t>(cap) * per + 128 * L.c_out) * L.osplit;
+        NAFP_CUDA(cudaMalloc(&s->x[l], x_elems * sizeof(__half)));
+        NAFP_CUDA(cudaMemset(s->x[l], 0, x_elems * sizeof(__half)));
+    }
+    NAFP_CUDA(cudaMalloc(&s->y, (static_cast<size_t>(cap) * ymax + 128 * 1024) * sizeof(__half)));
+    NAFP_CUDA(cudaMalloc(&s->stats, static_cast<size_t>(ENC_LAYERS) * cap * 2 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->part, static_cast<size_t>(cap) * 64 * CONV_EPI_PARTS * 2 * sizeof(float)));   // <= 64 row groups x parts float2 slots per segment
+    NAFP_CUDA(cudaMalloc(&s->mel, static_cast<size_t>(cap) * 8192 * sizeof(float)));
+    for (int b = 0; b < 2; ++b) NAFP_CUDA(cudaMalloc(&s->xin[b], static_cast<size_t>(cap) * 8000 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->emb, static_cast<size_t>(cap) * EMB * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->raw, static_cast<size_t>(cap) * EMB * sizeof(float)));
+    // activation tensor maps (rows past the live batch are masked by the epilogue)
+    for (int l = 1; l < ENC_LAYERS; ++l) {
+        const ConvGeom& L = s->g[l];
+        const uint64_t C = static_cast<uint64_t>(L.c_in) * L.ksplit, T = L.t_in, F = L.f_in, B = cap;
         uint64_t dims[5], str[5];
         uint32_t box[5];
         int rank;
@@ -697,38 +753,38 @@ static int encoder_init(nafp_ctx* ctx) {
         }
         NAFP_TRY(make_tensor_map(&s->tmA[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, s->x[l - 1], dims, str, box, nullptr,
                                  CU_TENSOR_MAP_SWIZZLE_128B));
-        const uint64_t wd[2] = {3 * C, static_cast<uint64_t>(L.c_out)};
-        const uint64_t ws[2] = {2, 3 * C * 2};
-        const uint32_t wb[2] = {64, static_cast<uint32_t>(L.nt)};
-        NAFP_TRY(make_tensor_map(&s->tmB[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, s->wt[l], wd, ws, wb, nullptr,
-                                 CU_TENSOR_MAP_SWIZZLE_128B));
     }
-    NAFP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
-    ctx->encoder = s;
+    s->cap = static_cast<int>(cap);
     return NAFP_OK;
 }
 
 void encoder_destroy(nafp_ctx* ctx) {
     EncoderState* s = ctx->encoder;
     if (!s) return;
+    encoder_release_arena(s);
     for (int l = 0; l < ENC_LAYERS; ++l) {
-        cudaFree(s->x[l]); cudaFree(s->bias[l]); cudaFree(s->ln_g[l]); cudaFree(s->ln_b[l]);
+        cudaFree(s->bias[l]); cudaFree(s->ln_g[l]); cudaFree(s->ln_b[l]);
         if (s->wt[l]) cudaFree(s->wt[l]);
     }
-    void* bufs[] = {s->w0, s->y, s->stats, s->part, s->raw, s->dw1, s->db1, s->dw2, s->db2, s->mel, s->xin, s->emb};
+    void* bufs[] = {s->w0, s->dw1, s->db1, s->dw2, s->db2};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (int b = 0; b < 2; ++b) {
+        if (s->ev_up[b]) cudaEventDestroy(s->ev_up[b]);
+        if (s->ev_free[b]) cudaEventDestroy(s->ev_free[b]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
     ctx->encoder = nullptr;
 }
 
-// one pass over n <= ENC_CHUNK segments; mel is either final (gmax == nullptr) or raw log-mel + group maxima
+// one pass over n <= cap segments (encoder_reserve); mel is either final (gmax == nullptr) or raw log-mel + group maxima
 static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, int64_t group_size, int64_t seg0, int n,
                         float* emb_dev) {
     EncoderState* s = ctx->encoder;
     cudaStream_t st = ctx->stream;
     for (int l = 0; l < ENC_LAYERS; ++l) {
         const ConvGeom& L = s->g[l];
-        float* stats = s->stats + static_cast<size_t>(l) * ENC_CHUNK * 2;
+        float* stats = s->stats + static_cast<size_t>(l) * s->cap * 2;
         const int per = L.ms * L.c_out;
         if (l == 0) {
             conv0_stats_kernel<<<dim3(8, n), 256, 0, st>>>(mel, gmax, group_size, n, s->w0, s->bias[0], s->part);
@@ -764,9 +820,10 @@ static int fingerprint_dev(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t
                            float* emb_dev) {
     EncoderState* s = ctx->encoder;
     // chunks are whole groups so that every group's batch-global max is complete (melspectrogram.py:108)
-    int64_t chunk = group_size <= ENC_CHUNK ? (ENC_CHUNK / group_size) * group_size : 0;
+    int64_t chunk = group_size <= ENC_CHUNK_MAX ? (ENC_CHUNK_MAX / group_size) * group_size : 0;
     NAFP_REQUIRE(chunk > 0, NAFP_ERR_UNSUPPORTED, "fingerprint: group_size %lld exceeds the %d-segment encoder pass",
-                 (long long)group_size, ENC_CHUNK);
+                 (long long)group_size, ENC_CHUNK_MAX);
+    NAFP_TRY(encoder_reserve(ctx, n_seg < chunk ? n_seg : chunk));
     const size_t elt = pcm16 ? sizeof(int16_t) : sizeof(float);
     for (int64_t s0 = 0; s0 < n_seg; s0 += chunk) {
         const int n = static_cast<int>(n_seg - s0 < chunk ? n_seg - s0 : chunk);
@@ -836,8 +893,9 @@ int nafp_encoder_forward(nafp_ctx* ctx, const float* mel_dev, int64_t n_seg, flo
                  "nafp_encoder_forward: bad arguments");
     NAFP_REQUIRE(ctx->encoder && ctx->encoder->weights, NAFP_ERR_STATE, "nafp_encoder_forward: call nafp_weights_load first");
     NAFP_CUDA(cudaSetDevice(ctx->device));
-    for (int64_t s0 = 0; s0 < n_seg; s0 += ENC_CHUNK) {
-        const int n = static_cast<int>(n_seg - s0 < ENC_CHUNK ? n_seg - s0 : ENC_CHUNK);
+    NAFP_TRY(encoder_reserve(ctx, n_seg < ENC_CHUNK_MAX ? n_seg : ENC_CHUNK_MAX));
+    for (int64_t s0 = 0; s0 < n_seg; s0 += ENC_CHUNK_MAX) {
+        const int n = static_cast<int>(n_seg - s0 < ENC_CHUNK_MAX ? n_seg - s0 : ENC_CHUNK_MAX);
         NAFP_TRY(encoder_pass(ctx, mel_dev + s0 * 8192, nullptr, 1, s0, n, emb_dev + s0 * EMB));
     }
     return NAFP_OK;
@@ -858,19 +916,35 @@ static int fingerprint_host(nafp_ctx* ctx, const void* x_host, bool pcm16, int64
     NAFP_REQUIRE(ctx->encoder && ctx->encoder->weights, NAFP_ERR_STATE, "nafp_fingerprint_host: call nafp_weights_load first");
     NAFP_CUDA(cudaSetDevice(ctx->device));
     EncoderState* s = ctx->encoder;
-    const int64_t chunk = group_size <= ENC_CHUNK ? (ENC_CHUNK / group_size) * group_size : 0;
+    const int64_t chunk = group_size <= ENC_CHUNK_MAX ? (ENC_CHUNK_MAX / group_size) * group_size : 0;
     NAFP_REQUIRE(chunk > 0, NAFP_ERR_UNSUPPORTED, "fingerprint: group_size %lld exceeds the %d-segment encoder pass",
-                 (long long)group_size, ENC_CHUNK);
+                 (long long)group_size, ENC_CHUNK_MAX);
+    NAFP_TRY(encoder_reserve(ctx, n_seg < chunk ? n_seg : chunk));      // before s->xin / s->emb are read below
     const size_t elt = pcm16 ? sizeof(int16_t) : sizeof(float);
-    for (int64_t s0 = 0; s0 < n_seg; s0 += chunk) {
+    const uint8_t* src = static_cast<const uint8_t*>(x_host);
+    auto upload = [&](int64_t s0, int b) -> cudaError_t {      // pass starting at s0 -> xin[b], on the copy stream
         const int64_t n = n_seg - s0 < chunk ? n_seg - s0 : chunk;
-        NAFP_CUDA(cudaMemcpyAsync(s->xin, static_cast<const uint8_t*>(x_host) + static_cast<size_t>(s0) * 8000 * elt,
-                                  static_cast<size_t>(n) * 8000 * elt, cudaMemcpyHostToDevice, ctx->stream));
-        NAFP_TRY(fingerprint_dev(ctx, s->xin, pcm16, n, group_size, s->emb));
+        cudaError_t e = cudaStreamWaitEvent(s->copy_stream, s->ev_free[b], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(s->xin[b], src + static_cast<size_t>(s0) * 8000 * elt, static_cast<size_t>(n) * 8000 * elt,
+                                cudaMemcpyHostToDevice, s->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(s->ev_up[b], s->copy_stream);
+        return e;
+    };
+    // the copy stream starts behind everything already queued on the compute stream (it may still read xin[0/1])
+    for (int b = 0; b < 2; ++b) NAFP_CUDA(cudaEventRecord(s->ev_free[b], ctx->stream));
+    if (n_seg > 0) NAFP_CUDA(upload(0, 0));
+    int b = 0;
+    for (int64_t s0 = 0; s0 < n_seg; s0 += chunk, b ^= 1) {
+        const int64_t n = n_seg - s0 < chunk ? n_seg - s0 : chunk;
+        if (s0 + chunk < n_seg) NAFP_CUDA(upload(s0 + chunk, b ^ 1));     // under this pass's kernels
+        NAFP_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev_up[b], 0));
+        NAFP_TRY(fingerprint_dev(ctx, s->xin[b], pcm16, n, group_size, s->emb));
+        NAFP_CUDA(cudaEventRecord(s->ev_free[b], ctx->stream));
         NAFP_CUDA(cudaMemcpyAsync(emb_host + s0 * EMB, s->emb, static_cast<size_t>(n) * EMB * sizeof(float),
                                   cudaMemcpyDeviceToHost, ctx->stream));
-        NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     return NAFP_OK;
 }
 

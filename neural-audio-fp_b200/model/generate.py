@@ -84,7 +84,7 @@ def _shard(n_batches, rank, world):
 
 
 def generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source_root_dir, output_root_dir, skip_dummy,
-                         rank=0, world_size=1, device=None, batches_per_call=8):
+                         rank=0, world_size=1, device=None, batches_per_call=64):
     """See the module docstring.  ``rank`` / ``world_size``: every rank fingerprints a contiguous range
     of whole TS_BATCH_SZ batches on its own GPU and writes its rows of the shared memmap."""
     m_pre, m_fp = build_fp(cfg, device=rank if device is None else device)

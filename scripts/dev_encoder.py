@@ -23,14 +23,15 @@ print("emb max abs err", np.abs(emb - ref).max(), "min cosine", (emb * ref).sum(
 emb2 = m_fp.fingerprint(x, B)
 print("fused vs split max diff", np.abs(emb2 - emb).max(), "fused vs ref", np.abs(emb2 - ref).max())
 # timing
-n = 1000
-xb = np.tile(x, (n // B + 1, 1))[:n]
-for _ in range(2): m_fp.fingerprint(xb, 125)
-t0 = time.time(); m_fp.fingerprint(xb, 125); dt = time.time() - t0
-print(f"e2e host->host {n} segs in {dt*1e3:.1f} ms -> {n/dt:.0f} seg/s")
-xd = ctx.malloc(xb.nbytes); ctx.h2d(xd, xb); ed = ctx.malloc(n * 512)
-for _ in range(2): check(lib.nafp_fingerprint(ctx.h, xd, n, 125, ed))
-ctx.sync(); ctx.timer_start()
-for _ in range(5): check(lib.nafp_fingerprint(ctx.h, xd, n, 125, ed))
-ms = ctx.timer_stop() / 5
-print(f"device {n} segs in {ms:.2f} ms -> {n/ms*1e3:.0f} seg/s = {n/ms*1e3*0.6072/1e3:.1f} TFLOP/s")
+for n in (1000, 4000, 8000):
+    xb = np.tile(x, (n // B + 1, 1))[:n]
+    for _ in range(2): m_fp.fingerprint(xb, 125)
+    t0 = time.time(); m_fp.fingerprint(xb, 125); dt = time.time() - t0
+    print(f"e2e host->host {n} segs in {dt*1e3:.1f} ms -> {n/dt:.0f} seg/s")
+    xd = ctx.malloc(xb.nbytes); ctx.h2d(xd, xb); ed = ctx.malloc(n * 512)
+    for _ in range(2): check(lib.nafp_fingerprint(ctx.h, xd, n, 125, ed))
+    ctx.sync(); ctx.timer_start()
+    for _ in range(5): check(lib.nafp_fingerprint(ctx.h, xd, n, 125, ed))
+    ms = ctx.timer_stop() / 5
+    print(f"device {n} segs in {ms:.2f} ms -> {n/ms*1e3:.0f} seg/s = {n/ms*1e3*0.6072/1e3:.1f} TFLOP/s")
+    ctx.free(xd); ctx.free(ed)
