@@ -35,7 +35,7 @@ typedef enum {
     NAFP_ERR_UNSUPPORTED = -4 /* valid in the reference but outside the hot path built here */
 } nafp_status;
 
-enum { NAFP_INDEX_FLAT_L2 = 0, NAFP_INDEX_IVFPQ = 1 };
+enum { NAFP_INDEX_FLAT_L2 = 0, NAFP_INDEX_IVFPQ = 1, NAFP_INDEX_IVF_FLAT = 2 };
 
 /* ------------------------------------------------------------------ library / context */
 int nafp_version(void);
@@ -121,12 +121,13 @@ int nafp_encoder_activation_host(nafp_ctx* ctx, int layer, int64_t n_seg, float*
 
 /* ------------------------------------------------------------------ index
  * Replaces the object returned by get_index() (eval/utils/get_index_faiss.py:10-121) for
- * index_type 'l2' (faiss.IndexFlatL2, :58) and 'ivfpq' (faiss.IndexIVFPQ(flat,d,256,64,8), :69-74).
+ * index_type 'l2' (faiss.IndexFlatL2, :58), 'ivfpq' (faiss.IndexIVFPQ(flat,d,256,64,8), :69-74) and
+ * 'ivf' (faiss.IndexIVFFlat(flat,d,400), :63-66; pq_m / pq_nbits are ignored for it).
  */
 int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int pq_nbits,
                       nafp_index** out);
 int nafp_index_destroy(nafp_index* idx);
-/* index.train(x) (get_index_faiss.py:113,116): no-op for FLAT_L2; k-means for IVFPQ. */
+/* index.train(x) (get_index_faiss.py:113,116): no-op for FLAT_L2; k-means for IVFPQ / IVF_FLAT. */
 int nafp_index_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed);
 /* index.add(x) (eval/eval_faiss.py:147-148): appends n rows; labels are insertion order. */
 int nafp_index_add(nafp_index* idx, const float* x_host, int64_t n);
@@ -135,6 +136,10 @@ int nafp_index_add_dev(nafp_index* idx, const float* x_dev, int64_t n);
  * e.g. to reuse one training across shards; import is only allowed on an empty index. */
 int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_host);
 int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const float* pq_host);
+/* IVF-Flat and IVF-PQ: the coarse quantizer alone ((nlist,128) float32); import only on an empty index
+ * (an IVF-Flat index counts as trained afterwards). */
+int nafp_index_ivf_get_coarse(nafp_index* idx, float* coarse_host);
+int nafp_index_ivf_set_coarse(nafp_index* idx, const float* coarse_host);
 /* pre-size the device store (optional; avoids regrowth copies for very large databases) */
 int nafp_index_reserve(nafp_index* idx, int64_t n_total);
 int64_t nafp_index_ntotal(nafp_index* idx);

@@ -1073,8 +1073,8 @@ extern "C" {
 int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int pq_nbits, nafp_index** out) {
     NAFP_REQUIRE(ctx && out, NAFP_ERR_INVALID, "nafp_index_create: NULL argument");
     *out = nullptr;
-    NAFP_REQUIRE(type == NAFP_INDEX_FLAT_L2 || type == NAFP_INDEX_IVFPQ, NAFP_ERR_UNSUPPORTED,
-                 "nafp_index_create: index type %d is outside the hot path (l2, ivfpq)", type);
+    NAFP_REQUIRE(type == NAFP_INDEX_FLAT_L2 || type == NAFP_INDEX_IVFPQ || type == NAFP_INDEX_IVF_FLAT, NAFP_ERR_UNSUPPORTED,
+                 "nafp_index_create: index type %d is not built (l2, ivfpq, ivf)", type);
     NAFP_REQUIRE(d == D128, NAFP_ERR_UNSUPPORTED, "nafp_index_create: d=%d; only d=128 (MODEL.EMB_SZ) is built", d);
     NAFP_CUDA(cudaSetDevice(ctx->device));
     nafp_index* idx = new nafp_index();
@@ -1087,9 +1087,10 @@ int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int p
         delete idx;
         return NAFP_ERR_CUDA;
     }
-    if (type == NAFP_INDEX_IVFPQ) {
-        int s = ivfpq_create(idx, nlist, pq_m, pq_nbits);
+    if (type != NAFP_INDEX_FLAT_L2) {
+        int s = type == NAFP_INDEX_IVFPQ ? ivfpq_create(idx, nlist, pq_m, pq_nbits) : ivfflat_create(idx, nlist);
         if (s != NAFP_OK) {
+            if (idx->ivf) ivfpq_destroy(idx);
             cudaFree(idx->maxn2);
             delete idx;
             return s;
@@ -1126,11 +1127,11 @@ int nafp_index_is_trained(nafp_index* idx);
 static int add_common(nafp_index* idx, const float* x, int64_t n, bool host) {
     NAFP_REQUIRE(idx && (n == 0 || x) && n >= 0, NAFP_ERR_INVALID, "nafp_index_add: bad arguments");
     NAFP_REQUIRE(idx->n + n < (1ll << 32), NAFP_ERR_UNSUPPORTED, "nafp_index_add: more than 2^32 rows per shard");
-    if (idx->type == NAFP_INDEX_IVFPQ)
-        NAFP_REQUIRE(nafp_index_is_trained(idx) == 1, NAFP_ERR_STATE, "nafp_index_add: IVFPQ index is not trained");
+    if (idx->type != NAFP_INDEX_FLAT_L2)
+        NAFP_REQUIRE(nafp_index_is_trained(idx) == 1, NAFP_ERR_STATE, "nafp_index_add: IVF index is not trained");
     const int64_t row0 = idx->n;
     NAFP_TRY(flat_add_dev(idx, x, n, host));
-    if (idx->type == NAFP_INDEX_IVFPQ) NAFP_TRY(ivfpq_add_rows(idx, row0, n));
+    if (idx->type != NAFP_INDEX_FLAT_L2) NAFP_TRY(ivfpq_add_rows(idx, row0, n));
     return NAFP_OK;
 }
 int nafp_index_add(nafp_index* idx, const float* x_host, int64_t n) { return add_common(idx, x_host, n, true); }
@@ -1163,7 +1164,7 @@ int nafp_index_set_label_offset(nafp_index* idx, int64_t offset) {
 int nafp_index_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
     NAFP_REQUIRE(idx && nq >= 0 && (nq == 0 || (q_dev && D_dev && I_dev)), NAFP_ERR_INVALID,
                  "nafp_index_search_dev: bad arguments");
-    if (idx->type == NAFP_INDEX_IVFPQ) return ivfpq_search_dev(idx, q_dev, nq, k, D_dev, I_dev);
+    if (idx->type != NAFP_INDEX_FLAT_L2) return ivfpq_search_dev(idx, q_dev, nq, k, D_dev, I_dev);
     return flat_search_dev(idx, q_dev, nq, k, D_dev, I_dev);
 }
 

@@ -14,6 +14,11 @@
 //           ADC(q, code) = |q - xhat|^2 (xhat = the row's reconstruction): a flat index over xhat (same row
 //           order) is searched with the tensor-core scan for the 64 nearest reconstructions, the candidates
 //           outside the nprobe nearest lists are dropped, and k survivors in order ARE the IVF-PQ answer.
+//
+// IVF-Flat ('ivf', faiss.IndexIVFFlat(IndexFlatL2(d), d, nlist=400), get_index_faiss.py:63-66) shares the coarse
+// quantizer, the probe and the filter: the exact flat scan of the index's own rows gives the 64 nearest rows,
+// the ones outside the probed lists are dropped; rows left with fewer than k answers get an exact scan of
+// their probed lists (ivfflat_scan_kernel).
 #include <algorithm>
 #include <cfloat>
 #include <climits>
@@ -34,6 +39,7 @@ constexpr int IVF_SCAN_CAP = 512;         // candidate buffer per (query, list) 
 
 struct IvfPq {
     int nlist = 256, m = 64, dsub = 2;
+    bool flat_lists = false;      // IVF-Flat: the lists hold the stored rows themselves (no product quantizer)
     bool trained = false;
     float* coarse = nullptr;      // [nlist][128]
     float* pq = nullptr;          // [m][256][dsub]
@@ -290,9 +296,11 @@ __global__ void ivf_scatter_kernel(const int32_t* __restrict__ assign, const uin
         __syncwarp();
         if (ok) {
             lids[pos] = static_cast<int32_t>(i);
-            const uint4* src = reinterpret_cast<const uint4*>(codes + i * m);
-            uint4* dst = reinterpret_cast<uint4*>(lcodes + pos * m);
-            for (int v = 0; v < m / 16; ++v) dst[v] = src[v];
+            if (codes) {                          // IVF-Flat lists carry row ids only
+                const uint4* src = reinterpret_cast<const uint4*>(codes + i * m);
+                uint4* dst = reinterpret_cast<uint4*>(lcodes + pos * m);
+                for (int v = 0; v < m / 16; ++v) dst[v] = src[v];
+            }
         }
     }
 }
@@ -435,6 +443,68 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
     }
 }
 
+// IVF-Flat: CTA (probe p, query row i) scans the stored rows of list l exactly (fp32), a warp per row
+__global__ void __launch_bounds__(256)
+ivfflat_scan_kernel(const float* __restrict__ q, int64_t nq, const int32_t* __restrict__ probes, int nprobe,
+                    const float* __restrict__ x32, const int32_t* __restrict__ lids, const int32_t* __restrict__ loff,
+                    int k, int64_t label_offset, float* __restrict__ partD, int64_t* __restrict__ partI) {
+    __shared__ uint64_t buf[IVF_SCAN_CAP];
+    __shared__ int cnt_s;
+    __shared__ unsigned long long thr_s;
+    const int p = blockIdx.x;
+    const int64_t i = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l = probes[i * nprobe + p];
+    float* outD = partD + (static_cast<int64_t>(p) * nq + i) * k;
+    int64_t* outI = partI + (static_cast<int64_t>(p) * nq + i) * k;
+    const int64_t lo = l >= 0 ? loff[l] : 0, hi = l >= 0 ? loff[l + 1] : 0;
+    if (hi <= lo) {
+        for (int j = tid; j < k; j += blockDim.x) { outD[j] = INFINITY; outI[j] = -1; }
+        return;
+    }
+    const float4 qv = reinterpret_cast<const float4*>(q + i * D128)[lane];
+    for (int e = tid; e < IVF_SCAN_CAP; e += blockDim.x) buf[e] = ~0ull;
+    if (tid == 0) { cnt_s = 0; thr_s = ~0ull; }
+    __syncthreads();
+    constexpr int ROWS_PER_WARP = 8;          // 64 rows per block iteration: <= 64 new keys between two prune checks
+    for (int64_t base = lo; base < hi; base += 8 * ROWS_PER_WARP) {
+#pragma unroll 4
+        for (int r = 0; r < ROWS_PER_WARP; ++r) {
+            const int64_t pos = base + warp * ROWS_PER_WARP + r;
+            if (pos < hi) {
+                const int32_t row = lids[pos];
+                const float4 xv = reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(row) * D128)[lane];
+                const float d0 = qv.x - xv.x, d1 = qv.y - xv.y, d2 = qv.z - xv.z, d3 = qv.w - xv.w;
+                float d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                if (lane == 0) {
+                    const uint64_t key = (static_cast<uint64_t>(__float_as_uint(d)) << 32) | static_cast<uint32_t>(row);
+                    if (key < thr_s) buf[atomicAdd(&cnt_s, 1)] = key;      // slot < CAP: pruned below before it can fill
+                }
+            }
+        }
+        __syncthreads();
+        if (cnt_s > IVF_SCAN_CAP - 8 * ROWS_PER_WARP) {
+            block_sort_asc_u64(buf, IVF_SCAN_CAP);
+            for (int e = k + tid; e < IVF_SCAN_CAP; e += blockDim.x) buf[e] = ~0ull;
+            if (tid == 0) { cnt_s = k; thr_s = buf[k - 1]; }
+            __syncthreads();
+        }
+    }
+    block_sort_asc_u64(buf, IVF_SCAN_CAP);
+    for (int j = tid; j < k; j += blockDim.x) {
+        const uint64_t key = buf[j];
+        if (key != ~0ull) {
+            outD[j] = __uint_as_float(static_cast<uint32_t>(key >> 32));
+            outI[j] = static_cast<int64_t>(static_cast<uint32_t>(key)) + label_offset;
+        } else {
+            outD[j] = INFINITY;
+            outI[j] = -1;
+        }
+    }
+}
+
 // xhat[row] = coarse[assign[row]] + concat_m pq[m][code[row][m]]; one warp per row, lane owns 4 dims
 __global__ void ivfpq_decode_kernel(const int32_t* __restrict__ assign, const uint8_t* __restrict__ codes, int64_t row0, int64_t n,
                                     const float* __restrict__ coarse, const float* __restrict__ pq, int m, int dsub,
@@ -509,6 +579,19 @@ __global__ void ivfpq_scatter_kernel(const float* __restrict__ Ds, const int64_t
 }
 
 // ------------------------------------------------------------------------------------------ host
+int ivfflat_create(nafp_index* idx, int nlist) {
+    NAFP_REQUIRE(nlist >= 1 && nlist <= IVF_MAX_NLIST, NAFP_ERR_INVALID, "ivf: nlist=%d outside [1,%d]", nlist, IVF_MAX_NLIST);
+    IvfPq* s = new IvfPq();
+    s->flat_lists = true;
+    s->nlist = nlist;
+    s->m = 0;
+    s->dsub = 0;
+    idx->ivf = s;                  // before the first fallible call: nafp_index_destroy releases it
+    NAFP_CUDA(cudaMalloc(&s->coarse, static_cast<size_t>(nlist) * D128 * sizeof(float)));
+    NAFP_CUDA(cudaMalloc(&s->loff, (nlist + 1) * sizeof(int32_t)));
+    return NAFP_OK;
+}
+
 int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits) {
     NAFP_REQUIRE(nbits == 8, NAFP_ERR_UNSUPPORTED, "ivfpq: nbits=%d (only 8, as in the reference)", nbits);
     NAFP_REQUIRE(nlist >= 1 && nlist <= IVF_MAX_NLIST, NAFP_ERR_INVALID, "ivfpq: nlist=%d outside [1,%d]", nlist, IVF_MAX_NLIST);
@@ -543,7 +626,7 @@ int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
     nafp_ctx* ctx = idx->ctx;
     NAFP_CUDA(cudaSetDevice(ctx->device));
     // faiss-style subsampling: at most 256 training points per centroid
-    const int64_t max_pts = 256ll * std::max(s->nlist, PQ_KSUB);
+    const int64_t max_pts = 256ll * (s->flat_lists ? s->nlist : std::max(s->nlist, PQ_KSUB));
     std::vector<int64_t> rows(n);
     std::iota(rows.begin(), rows.end(), 0);
     int64_t nt = n;
@@ -565,6 +648,14 @@ int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
     NAFP_CUDA(cudaMalloc(&a_dev, nt * sizeof(int32_t)));
     NAFP_CUDA(cudaMemcpy(x_dev, xt.data(), xt.size() * sizeof(float), cudaMemcpyHostToDevice));
     NAFP_TRY(run_kmeans(ctx, x_dev, nt, D128, D128, s->nlist, s->coarse, a_dev, 25, static_cast<uint64_t>(seed) + 1));
+    if (s->flat_lists) {
+        NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(x_dev);
+        cudaFree(r_dev);
+        cudaFree(a_dev);
+        s->trained = true;
+        return NAFP_OK;
+    }
     // final assignment with the final centroids, then residuals
     kmeans_assign_kernel<<<static_cast<unsigned>((nt + 7) / 8), 256, 8 * D128 * sizeof(float), ctx->stream>>>(
         x_dev, nt, D128, D128, s->coarse, s->nlist, a_dev, nullptr);
@@ -590,10 +681,11 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
         int32_t* a = nullptr;
         uint8_t* c = nullptr;
         NAFP_CUDA(cudaMalloc(&a, static_cast<size_t>(idx->cap) * sizeof(int32_t)));
-        NAFP_CUDA(cudaMalloc(&c, static_cast<size_t>(idx->cap) * s->m));
+        if (!s->flat_lists) NAFP_CUDA(cudaMalloc(&c, static_cast<size_t>(idx->cap) * s->m));
         if (row0 > 0) {
             NAFP_CUDA(cudaMemcpyAsync(a, s->assign, static_cast<size_t>(row0) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-            NAFP_CUDA(cudaMemcpyAsync(c, s->codes, static_cast<size_t>(row0) * s->m, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (!s->flat_lists)
+                NAFP_CUDA(cudaMemcpyAsync(c, s->codes, static_cast<size_t>(row0) * s->m, cudaMemcpyDeviceToDevice, ctx->stream));
             NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
         }
         if (s->assign) cudaFree(s->assign);
@@ -601,6 +693,14 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
         s->assign = a;
         s->codes = c;
         s->cap = idx->cap;
+    }
+    if (s->flat_lists) {               // list of every new row = its nearest coarse centroid (ties -> lower id)
+        kmeans_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 8 * D128 * sizeof(float), ctx->stream>>>(
+            idx->x32 + row0 * D128, n, D128, D128, s->coarse, s->nlist, s->assign + row0, nullptr);
+        ctx->launches++;
+        NAFP_CUDA(cudaGetLastError());
+        s->dirty = true;
+        return NAFP_OK;
     }
     int64_t blocks = (n + 7) / 8;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
@@ -629,7 +729,7 @@ static int build_lists(nafp_index* idx) {
         if (s->lcodes) cudaFree(s->lcodes);
         if (s->lids) cudaFree(s->lids);
         s->lcodes = nullptr; s->lids = nullptr; s->sorted_cap = 0;
-        NAFP_CUDA(cudaMalloc(&s->lcodes, static_cast<size_t>(idx->cap) * s->m));
+        if (!s->flat_lists) NAFP_CUDA(cudaMalloc(&s->lcodes, static_cast<size_t>(idx->cap) * s->m));
         NAFP_CUDA(cudaMalloc(&s->lids, static_cast<size_t>(idx->cap) * sizeof(int32_t)));
         s->sorted_cap = idx->cap;
     }
@@ -694,14 +794,19 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
         s->scratch_nq = cq; s->scratch_nprobe = cp; s->scratch_k = ck;
     }
     const size_t lut_bytes = static_cast<size_t>(s->m) * PQ_KSUB * sizeof(float);
-    NAFP_CUDA(cudaFuncSetAttribute(ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lut_bytes)));
+    if (!s->flat_lists)
+        NAFP_CUDA(cudaFuncSetAttribute(ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lut_bytes)));
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
         const int64_t nc = nq - q0 < chunk ? nq - q0 : chunk;
         const float* qp = q_dev + q0 * D128;
         ivfpq_probe_kernel<<<static_cast<unsigned>((nc + 7) / 8), 256, 0, ctx->stream>>>(qp, nc, s->coarse, s->nlist, nprobe, s->probes);
-        ivfpq_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, lut_bytes, ctx->stream>>>(
-            qp, nc, s->coarse, s->pq, s->m, s->dsub, s->probes, nprobe, s->lcodes, s->lids, s->loff, k, idx->label_offset,
-            s->partD, s->partI);
+        if (s->flat_lists)
+            ivfflat_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, 0, ctx->stream>>>(
+                qp, nc, s->probes, nprobe, idx->x32, s->lids, s->loff, k, idx->label_offset, s->partD, s->partI);
+        else
+            ivfpq_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, lut_bytes, ctx->stream>>>(
+                qp, nc, s->coarse, s->pq, s->m, s->dsub, s->probes, nprobe, s->lcodes, s->lids, s->loff, k, idx->label_offset,
+                s->partD, s->partI);
         topk_merge_kernel<<<static_cast<unsigned>(nc), 128, 0, ctx->stream>>>(s->partD, s->partI, nprobe, nc, k, D_dev + q0 * k,
                                                                               I_dev + q0 * k);
         ctx->launches += 3;
@@ -720,7 +825,7 @@ int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, flo
     const int nprobe = idx->nprobe < s->nlist ? idx->nprobe : s->nlist;
     NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
                  "ivfpq search: need k <= %d and nprobe*k <= 2048 (nprobe %d, k %d)", MAX_K, nprobe, k);
-    idx->host_rows += nq;
+    if (!s->flat_lists) idx->host_rows += nq;          // (the flat scan of an IVF-Flat index counts its own rows)
     if (k > RECON_K / 2 || nq >= (1ll << 31)) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
 
     // 1. exact top-RECON_K over the reconstructed rows (tensor-core scan + fp32 re-rank)
@@ -748,8 +853,16 @@ int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, flo
     }
     int32_t* redo_count = s->redo_rows + s->redo_cap;
     NAFP_CUDA(cudaMemsetAsync(redo_count, 0, sizeof(int32_t), ctx->stream));
-    s->recon->search_rows = idx->search_rows;
-    NAFP_TRY(flat_search_dev(s->recon, q_dev, nq, RECON_K, s->candD, s->candI));
+    if (s->flat_lists) {               // the stored rows are the "reconstructions": scan the index itself
+        const int64_t off = idx->label_offset;      // the filter wants local rows and adds the offset itself
+        idx->label_offset = 0;
+        const int st = flat_search_dev(idx, q_dev, nq, RECON_K, s->candD, s->candI);
+        idx->label_offset = off;
+        NAFP_TRY(st);
+    } else {
+        s->recon->search_rows = idx->search_rows;
+        NAFP_TRY(flat_search_dev(s->recon, q_dev, nq, RECON_K, s->candD, s->candI));
+    }
     // 2. the nprobe nearest lists of every row, 3. keep the candidates that live in them
     ivfpq_probe_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, 0, ctx->stream>>>(q_dev, nq, s->coarse, s->nlist, nprobe, probes_all);
     ivfpq_filter_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, 0, ctx->stream>>>(s->candD, s->candI, nq, k, probes_all, nprobe,
@@ -790,8 +903,27 @@ int nafp_index_is_trained(nafp_index* idx) {
     return idx->ivf && idx->ivf->trained ? 1 : 0;
 }
 
+int nafp_index_ivf_get_coarse(nafp_index* idx, float* coarse_host) {
+    NAFP_REQUIRE(idx && idx->ivf && coarse_host, NAFP_ERR_INVALID, "nafp_index_ivf_get_coarse: not an IVF index");
+    IvfPq* s = idx->ivf;
+    NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "nafp_index_ivf_get_coarse: index is not trained");
+    NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
+    NAFP_CUDA(cudaMemcpy(coarse_host, s->coarse, static_cast<size_t>(s->nlist) * D128 * sizeof(float), cudaMemcpyDeviceToHost));
+    return NAFP_OK;
+}
+
+int nafp_index_ivf_set_coarse(nafp_index* idx, const float* coarse_host) {
+    NAFP_REQUIRE(idx && idx->ivf && coarse_host, NAFP_ERR_INVALID, "nafp_index_ivf_set_coarse: not an IVF index");
+    NAFP_REQUIRE(idx->n == 0, NAFP_ERR_STATE, "nafp_index_ivf_set_coarse: index already holds rows");
+    IvfPq* s = idx->ivf;
+    NAFP_CUDA(cudaMemcpy(s->coarse, coarse_host, static_cast<size_t>(s->nlist) * D128 * sizeof(float), cudaMemcpyHostToDevice));
+    if (s->flat_lists) s->trained = true;
+    return NAFP_OK;
+}
+
 int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_host) {
-    NAFP_REQUIRE(idx && idx->ivf && coarse_host && pq_host, NAFP_ERR_INVALID, "nafp_index_ivfpq_get_params: not an IVF-PQ index");
+    NAFP_REQUIRE(idx && idx->ivf && !idx->ivf->flat_lists && coarse_host && pq_host, NAFP_ERR_INVALID,
+                 "nafp_index_ivfpq_get_params: not an IVF-PQ index");
     IvfPq* s = idx->ivf;
     NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "nafp_index_ivfpq_get_params: index is not trained");
     NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
@@ -801,7 +933,8 @@ int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_h
 }
 
 int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const float* pq_host) {
-    NAFP_REQUIRE(idx && idx->ivf && coarse_host && pq_host, NAFP_ERR_INVALID, "nafp_index_ivfpq_set_params: not an IVF-PQ index");
+    NAFP_REQUIRE(idx && idx->ivf && !idx->ivf->flat_lists && coarse_host && pq_host, NAFP_ERR_INVALID,
+                 "nafp_index_ivfpq_set_params: not an IVF-PQ index");
     NAFP_REQUIRE(idx->n == 0, NAFP_ERR_STATE, "nafp_index_ivfpq_set_params: index already holds rows");
     IvfPq* s = idx->ivf;
     NAFP_CUDA(cudaMemcpy(s->coarse, coarse_host, static_cast<size_t>(s->nlist) * D128 * sizeof(float), cudaMemcpyHostToDevice));

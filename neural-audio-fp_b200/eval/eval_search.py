@@ -127,7 +127,7 @@ def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_t
 @click.option('--emb_dummy_dir', default=None, type=click.STRING,
               help="Specify a directory containing 'dummy_db.mm' and 'dummy_db_shape.npy' to use. Default is EMB_DIR.")
 @click.option('--index_type', '-i', default='ivfpq', type=click.STRING,
-              help="Index type must be one of {'L2', 'IVFPQ'} ('IVF', 'IVFPQ-RR', 'IVFPQ-ONDISK', 'HNSW' are not built).")
+              help="Index type must be one of {'L2', 'IVF', 'IVFPQ'} ('IVFPQ-RR', 'IVFPQ-ONDISK', 'HNSW' are not built).")
 @click.option('--nogpu', default=False, is_flag=True, help='Refused: this build has no CPU search path.')
 @click.option('--max_train', default=1e7, type=click.INT, help='Max number of items for index training. Default is 1e7.')
 @click.option('--test_seq_len', default='1 3 5 9 11 19', type=click.STRING,

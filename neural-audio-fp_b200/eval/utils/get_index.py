@@ -4,8 +4,9 @@ libnafp instead of faiss.
 ``get_index(index_type, train_data, train_data_shape, use_gpu, max_nitem_train)`` returns an object
 with the faiss surface the reference uses: ``train(x)``, ``add(x)``, ``ntotal``, ``nprobe``
 (attribute), ``search(q, k) -> (D, I)`` (squared-L2 ascending, int64 labels, -1 padding),
-``reconstruct_n(i0, n)``.  Index types outside the hot path ('ivf', 'ivfpq-rr', 'ivfpq-ondisk',
-'hnsw') raise NotImplementedError, like the reference does for the modes it cannot serve.
+``reconstruct_n(i0, n)``.  Built: 'l2', 'ivfpq' (the hot path) and 'ivf' (IndexIVFFlat, nlist 400).
+'ivfpq-rr', 'ivfpq-ondisk' and 'hnsw' raise NotImplementedError, like the reference does for the modes
+it cannot serve.
 """
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ import numpy as np
 
 from ..._lib import Context, NafpError, check, lib, ptr
 
-FLAT_L2, IVFPQ = 0, 1
+FLAT_L2, IVFPQ, IVF_FLAT = 0, 1, 2
 _ADD_CHUNK = 1 << 20      # rows per host->device copy (memmaps are read chunk by chunk)
 
 
@@ -72,6 +73,18 @@ class Index:
         pq = np.empty((self.pq_m, 256, 128 // self.pq_m), np.float32)
         check(lib.nafp_index_ivfpq_get_params(self.h, ptr(coarse), ptr(pq)))
         return coarse, pq
+
+    def ivf_coarse(self):
+        """(nlist,128) coarse centroids of a trained IVF-Flat / IVF-PQ index."""
+        coarse = np.empty((self.nlist, 128), np.float32)
+        check(lib.nafp_index_ivf_get_coarse(self.h, ptr(coarse)))
+        return coarse
+
+    def set_ivf_coarse(self, coarse):
+        coarse = _f32c(coarse)
+        if coarse.shape != (self.nlist, 128):
+            raise ValueError(f"expected ({self.nlist}, 128) centroids")
+        check(lib.nafp_index_ivf_set_coarse(self.h, ptr(coarse)))
 
     def set_ivfpq_params(self, coarse, pq):
         coarse, pq = _f32c(coarse), _f32c(pq)
@@ -159,8 +172,11 @@ def get_index(index_type, train_data, train_data_shape, use_gpu=True, max_nitem_
     elif mode == 'ivfpq':
         # reference: code_sz 64, n_centroids 256, nbits 8 (get_index_faiss.py:69-74)
         index = Index(IVFPQ, d, nlist=256, pq_m=64, pq_nbits=8, device=device)
-    elif mode in ('ivf', 'ivfpq-rr', 'ivfpq-ondisk', 'hnsw'):
-        raise NotImplementedError(f"index_type '{mode}' is outside the B200 hot path (l2, ivfpq)")
+    elif mode == 'ivf':
+        # reference: IndexIVFFlat, nlist 400 (get_index_faiss.py:63-66)
+        index = Index(IVF_FLAT, d, nlist=400, device=device)
+    elif mode in ('ivfpq-rr', 'ivfpq-ondisk', 'hnsw'):
+        raise NotImplementedError(f"index_type '{mode}' is not built (l2, ivfpq, ivf)")
     else:
         raise ValueError(mode)
 

@@ -109,3 +109,69 @@ def test_ivfpq_untrained_add_is_refused():
     g = Index(IVFPQ, 128)
     with pytest.raises(NafpError):
         g.add(np.zeros((4, 128), np.float32))
+
+
+@pytest.mark.parametrize("nlist,nprobe,k", [(400, 40, 20), (400, 2, 20), (64, 64, 5), (100, 10, 40)])
+def test_ivf_flat_same_centroids_matches_oracle(nlist, nprobe, k):
+    """index_type 'ivf' (faiss.IndexIVFFlat, nlist 400, nprobe 40): with the same coarse centroids the CUDA index
+    returns the oracle's rows -- through the scan + probed-list filter (most rows at nprobe 40), through the
+    exact list scan (few probes: most rows lack k probed rows among their 64 nearest) and for k above the fast
+    path's limit."""
+    from nafp_b200 import synth
+    from nafp_b200.eval.utils.get_index import IVF_FLAT, Index
+    from oracle.ivf_flat_index import IVFFlat
+    dummy, db, query = synth.synth_search_set(20000, 590, seed=27)
+    g = Index(IVF_FLAT, 128, nlist=nlist)
+    assert not g.is_trained
+    g.train(dummy, seed=99)
+    assert g.is_trained
+    g.add(dummy)
+    g.add(db)
+    g.nprobe = nprobe
+    o = IVFFlat(128, nlist)
+    o.set_coarse(g.ivf_coarse())
+    o.add(dummy)
+    o.add(db)
+    o.nprobe = nprobe
+    q = query[:96]
+    Dg, Ig = g.search(q, k)
+    Do, Io = o.search(q, k)
+    fin = np.isfinite(Do)
+    assert (np.isfinite(Dg) == fin).all() and ((Ig < 0) == (Io < 0)).all()
+    np.testing.assert_allclose(Dg[fin], Do[fin], rtol=0, atol=2e-5)
+    same = Ig == Io
+    assert same.mean() >= 0.99
+    for r, c in np.argwhere(~same):            # only permutations among (near-)equal distances
+        assert abs(Dg[r, c] - Do[r, c]) < 2e-5 and Ig[r, c] in Io[r]
+
+
+def test_ivf_flat_through_get_index_and_matcher():
+    """get_index('ivf', ...) trains nlist 400 on the dummy rows, nprobe 40; the sequence matcher on top of it
+    agrees with the oracle index holding the same centroids."""
+    from nafp_b200 import synth
+    from nafp_b200.eval.utils.get_index import get_index
+    from oracle import seq_match
+    from oracle.ivf_flat_index import IVFFlat
+    dummy, db, query = synth.synth_search_set(30000, 1180, seed=31)
+    g = get_index('ivf', dummy, dummy.shape, True, 1e7)
+    assert g.nlist == 400 and g.nprobe == 40 and g.is_trained
+    g.add(dummy)
+    g.add(db)
+    o = IVFFlat(128, 400)
+    o.set_coarse(g.ivf_coarse())
+    o.add(dummy)
+    o.add(db)
+    o.nprobe = 40
+    ids = np.arange(0, 1100, 37, dtype=np.int64)
+    lens = [1, 3, 5, 9]
+    pred_g, _ = g.seq_match(query, ids, lens, 20)
+    raw_o, pred_o = seq_match.evaluate(o, query, np.concatenate([dummy, db]), len(dummy), ids, lens, 20)
+    assert (pred_g[:, :, 0] == np.asarray(pred_o)[:, :, 0]).all()
+
+
+def test_ivf_flat_untrained_add_is_refused():
+    from nafp_b200._lib import NafpError
+    from nafp_b200.eval.utils.get_index import IVF_FLAT, Index
+    g = Index(IVF_FLAT, 128, nlist=400)
+    with pytest.raises(NafpError):
+        g.add(np.zeros((4, 128), np.float32))

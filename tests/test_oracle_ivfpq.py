@@ -39,3 +39,37 @@ def test_ivfpq_recall_against_exact_search():
     small.nprobe = 16
     Ds, Is = small.search(query[:2], 20)
     assert (Is[:, 5:] == -1).all() and np.isinf(Ds[:, 5:]).all() and set(Is[0, :5]) == set(range(5))
+
+
+def test_ivf_flat_all_lists_equals_exact_search_and_fewer_probes_lose_recall():
+    """IVF-Flat restatement (index_type 'ivf'): probing every list IS the exact search; probing a few can only
+    lose rows; labels are insertion order with -1 padding."""
+    from oracle.ivf_flat_index import IVFFlat
+    dummy, db, query = synth.synth_search_set(5000, 590, seed=14)
+    idx = IVFFlat(128, nlist=20)
+    idx.train(dummy)
+    idx.add(dummy)
+    idx.add(db)
+    assert idx.ntotal == 5590 and idx.assign.min() >= 0 and idx.assign.max() < 20
+    flat = FlatL2(128)
+    flat.add(dummy)
+    flat.add(db)
+    De, Ie = flat.search(query[:40], 20)
+    idx.nprobe = 20
+    D, I = idx.search(query[:40], 20)
+    assert (I == Ie).all()
+    np.testing.assert_allclose(D, De, atol=2e-6)
+    idx.nprobe = 2
+    D2, I2 = idx.search(query[:40], 20)
+    assert (np.diff(D2, axis=1) >= 0).all()
+    assert (D2 >= D - 1e-6).all()                         # a subset of the rows: every rank can only get worse
+    assert 0.3 <= (I2[:, 0] == Ie[:, 0]).mean() <= 1.0
+    for r in range(5):                                    # every returned row lives in a probed list
+        probes = np.argsort(idx._coarse_dist(query[r:r + 1]), 1, kind="stable")[0, :2]
+        assert np.isin(idx.assign[I2[r]], probes).all()
+    small = IVFFlat(128, nlist=20)
+    small.set_coarse(idx.coarse)
+    small.add(dummy[:5])
+    small.nprobe = 20
+    Ds, Is = small.search(query[:2], 20)
+    assert (Is[:, 5:] == -1).all() and np.isinf(Ds[:, 5:]).all() and set(Is[0, :5]) == set(range(5))
