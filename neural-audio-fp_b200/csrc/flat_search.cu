@@ -26,6 +26,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
 #include "index.h"
 #include "ptx.cuh"
 
@@ -112,6 +114,7 @@ constexpr int BOX_BYTES = TILE_ROWS * 128;                 // 16 KB per TMA box 
 constexpr int Q_KB_BYTES = NQ_MAX * 128;                   // 32 KB: one K block of the query operand
 constexpr int Q_BYTES_MAX = 2 * Q_KB_BYTES;                // 64 KB
 constexpr int H_RING = 4;                               // tiles of 0.5|x|^2 kept in shared memory
+constexpr int WARM_TILES = 8;                           // tiles every CTA scans max-only before it uses thresholds
 constexpr int SCAN_SMEM = Q_BYTES_MAX + RING_SLOTS * SLOT_BYTES + H_RING * SCAN_TILE * 4 + 2 * NQ_MAX * 4 + 256 + 1024;
 constexpr int NEG_INF_ORD = static_cast<int>(0x807FFFFFu);  // f2ord(-inf)
 static_assert(PART_COLS == 64, "epilogue reads two 32-column chunks per unit");
@@ -133,6 +136,11 @@ __device__ __forceinline__ void smem_red_max(int* p, int v) {
 __device__ __forceinline__ int smem_atom_inc(int* p) {
     int old;
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
+}
+__device__ __forceinline__ int smem_atom_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
 }
 __device__ __forceinline__ int smem_ld_volatile(const int* p) {
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1)
 flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  const float* __restrict__ hn, int32_t* __restrict__ tile_counter, int64_t n_search, int n_tiles, int nq,
                  int n_half, int kg, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
-                 int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first) {
+                 int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first, int tune) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_s = smem;                                   // [kb 2][256 query rows][128 B]
@@ -188,10 +196,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int G = gridDim.x;
     const int cta = blockIdx.x;
-    // Work items of a CTA: tile `cta` (scanned max-only), then tiles handed out by a global counter
-    // (SMs do not all stream at the same rate: with a static split the slowest CTA finished 35 % after the
-    // fastest), then tile `cta` again (with thresholds), then the end marker.  The TMA producer draws the
-    // tiles and tells the MMA issuer and the epilogue through bars->tile_of.
+    // Work items of a CTA: `warm` tiles cta, cta + G, ... scanned max-only (their exact maxima seed the shared
+    // thresholds, which are ready -- no wait -- when the last of them is done; a row scanned at tile t survives
+    // with probability ~ kg / (rows seen so far), so the first tiles of a pass would otherwise append, and pay
+    // for, half of all survivors), then tiles handed out by a global counter (SMs do not all stream at the same
+    // rate: with a static split the slowest CTA finished 35 % after the fastest), then the warm tiles again
+    // (with thresholds), then the end marker.  The TMA producer draws the tiles and tells the MMA issuer and
+    // the epilogue through bars->tile_of.
+    const int warm = (tune & 2) ? 1 : max(1, min(WARM_TILES, n_tiles / G));
 
     for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
         lmax_s[i] = INT_MIN;
@@ -230,8 +242,8 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int r0 = 0; r0 < q_rows; r0 += 32)
                     tma_load_2d(q_s + kb * Q_KB_BYTES + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
             int tile = cta;
-            bool revisited = false;
-            int nxt = G + atomicAdd(tile_counter, 1);           // drawn one item ahead: the round trip hides behind the loads
+            int revisit = -1;                                   // >= 0: index of the warm tile being revisited
+            int nxt = warm * G + atomicAdd(tile_counter, 1);    // drawn one item ahead: the round trip hides behind the loads
             for (int i = 0;; ++i) {
                 const int kc0 = 2 * i;
                 const uint32_t ph = (kc0 / RING_SLOTS) & 1;
@@ -256,14 +268,14 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     tma_load_2d(dst, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE);
                     tma_load_2d(dst + BOX_BYTES, &tmap_db, &bars->full[s], kb * 64, tile * SCAN_TILE + TILE_ROWS);
                 }
-                if (revisited) {
-                    tile = -1;
-                } else if (nxt < n_tiles) {
+                if (i + 1 < warm) {
+                    tile = cta + (i + 1) * G;
+                } else if (revisit < 0 && nxt < n_tiles) {
                     tile = nxt;
-                    nxt = G + atomicAdd(tile_counter, 1);
+                    nxt = warm * G + atomicAdd(tile_counter, 1);
                 } else {
-                    tile = cta;
-                    revisited = true;
+                    ++revisit;
+                    tile = revisit < warm ? cta + revisit * G : -1;
                 }
             }
         }
@@ -392,13 +404,22 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + part * PART_COLS;
         uint32_t uc = 0;
 
-        // ---- item 0 (tile `cta`) is scanned "max-only": its exact scores feed the running maxima from
-        // which the shared thresholds are built; the tile comes back with thresholds as the last item.
-        {
-            const uint32_t row0 = static_cast<uint32_t>(cta) * SCAN_TILE + part * PART_COLS;
+        // ---- items 0 .. warm-1 (tiles cta, cta + G, ...) are scanned "max-only": their exact scores feed the
+        // running maxima from which the shared thresholds are built; they come back, with thresholds, as the
+        // last items.
+        for (int w = 0; w < warm; ++w) {
+            const uint32_t row0 = static_cast<uint32_t>(cta + w * G) * SCAN_TILE + part * PART_COLS;
+            const float* h_part = h_s + (w % H_RING) * SCAN_TILE + part * PART_COLS;
+            // a tile of searchable rows only: chunk maximum - max 0.5|x|^2 of the warp's 64 rows (a lower bound of
+            // the best score, exact for unit-norm rows); a tile with halo / padding rows: exact, column by column
+            const bool edge = (static_cast<uint32_t>(cta + w * G) + 1u) * SCAN_TILE > ns32 || (tune & 4);
+            float hx = 0.f;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
                 mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
+                if (hq == 0 && !edge)
+                    hx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(h_part[lane], h_part[32 + lane])))) *
+                         (1.f + 1.f / 1048576.f);
                 tc_fence_after();
                 float munit = NEG_INF;
 #pragma unroll 1
@@ -406,11 +427,23 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     uint32_t v[32];
                     tmem_ld_32x32(tlane + acc * SCAN_TILE + c * 32, v);
                     tc_wait_ld();
-                    const float* hc = h_s + part * PART_COLS + c * 32;          // h ring entry 0
-                    const int nvalid = static_cast<int>(min(ns32 - min(ns32, row0 + c * 32), 32u));   // rows < n_search
+                    if (!edge) {
+                        float gm[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) munit = fmaxf(munit, __uint_as_float(v[j]) - hc[j]);
+                        for (int g = 0; g < 4; ++g) {
+                            float m = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                            m = fmax3(m, __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
+                            m = fmax3(m, __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
+                            gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+                        }
+                        munit = fmaxf(munit, fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]) - hx);
+                    } else {
+                        const float* hc = h_part + c * 32;
+                        const int nvalid = static_cast<int>(min(ns32 - min(ns32, row0 + c * 32), 32u));   // rows < n_search
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) munit = fmaxf(munit, __uint_as_float(v[j]) - hc[j]);
+                    }
                 }
                 if (hq == 0 ? active[0] : active[1]) smem_red_max(&lmax_s[hq * 128 + qd * 32 + lane], f2ord(munit));
                 tc_fence_before();
@@ -418,7 +451,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 mbar_arrive_lane0(&bars->tempty[acc], lane);
             }
             publish_maxima();
-            stamp(0);
+            if (w == 0) stamp(0);
         }
         // ---- wait (bounded) for the thresholds of this warp's queries
         {
@@ -434,15 +467,18 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // answers those queries
             stamp(1);
         }
-        // ---- the items the producer draws for this CTA, ending with tile `cta` again and the end marker
-        for (int i = 1;; ++i) {
+        // ---- the items the producer draws for this CTA, ending with the warm tiles again and the end marker
+        for (int i = warm;; ++i) {
             int tg[2] = {INT_MIN, INT_MIN};
-            const bool rf = i > 1 && (i < 32 || (i & 3) == 0);      // loads issued now, consumed after the tile
+            // one refresh every four tiles: a coherent load takes ~2 us under the scan's own traffic -- longer than a
+            // tile -- and after the warm tiles the thresholds move slowly (refreshing every tile cost 8 % of a
+            // 7 M-row pass).  Loads issued now, consumed after the tile.
+            const bool rf = i > warm && (((tune & 8) && i < warm + 32) || (i & 3) == 0);
             if (rf) load_thresholds(tg);
             const float* h_part = h_s + (i % H_RING) * SCAN_TILE + part * PART_COLS;
             uint32_t row0 = 0;
-            float hm = 0.f;
-            bool end = false;
+            float hm = 0.f, hx = 0.f;
+            bool end = false, edge = false;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
                 mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
@@ -458,6 +494,12 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const float hmin_w =
                         __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(h_part[lane], h_part[32 + lane]))));
                     hm = hmin_w * (1.f - 1.f / 1048576.f);
+                    // largest 0.5|x|^2 of the same rows: v - hx is a lower bound of the score behind a chunk maximum v
+                    const float hmax_w =
+                        __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(h_part[lane], h_part[32 + lane]))));
+                    hx = hmax_w * (1.f + 1.f / 1048576.f);
+                    // the tile holds rows that do not take part in the search (halo, padding): exact per-column path
+                    edge = (static_cast<uint32_t>(tile) + 1u) * SCAN_TILE > ns32 || (tune & 4);
                 }
                 const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
                 tc_fence_after();
@@ -479,24 +521,50 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const float ma = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
                     const bool fired = ma > tp;
                     if (__any_sync(0xffffffffu, fired)) {
-                        // rare: this lane's query has a score above the prefilter among the 32 columns;
-                        // only the 8-column groups whose maximum fired are looked at
-                        if (fired) {
-                            const int q = hq * 128 + qd * 32 + lane;
-                            const float te = hq == 0 ? t_exact[0] : t_exact[1];
-                            const float* hc = h_part + c * 32;
+                        // rare -- except in the first thresholded tiles of a pass, while the thresholds are still
+                        // loose: the path must be SHORT (the first version inlined 32 predicated append bodies,
+                        // 14 KB of branchy code).  Bit mask of this lane's columns above its prefilter; the pool
+                        // only carries row ids (flat_select re-scores every survivor exactly), and the running
+                        // maximum takes the lower bound  chunk maximum - max 0.5|x|^2  -- a bound that is too
+                        // low or too high can only move the threshold, never the answer (flat_select proves it).
+                        uint32_t m = 0;
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (gm[g] > tp) {
-#pragma unroll
-                                    for (int j = 8 * g; j < 8 * g + 8; ++j)
-                                        if (__uint_as_float(v[j]) > tp)
-                                            scan_append(__uint_as_float(v[j]), hc[j], te, row0 + c * 32 + j, ns32, &cnt_s[q], &lmax_s[q],
-                                                        my_pool + q * POOL_CAP);
+                        for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > tp) ? (1u << j) : 0u;
+                        const int q = hq * 128 + qd * 32 + lane;
+                        if (!edge) {
+                            if (fired) {
+                                smem_red_max(&lmax_s[q], f2ord(ma - hx));
+                                int pos = smem_atom_add(&cnt_s[q], __popc(m));
+                                uint64_t* pq = my_pool + q * POOL_CAP;
+                                const uint32_t rbase = row0 + c * 32;
+                                while (m) {
+                                    const int j = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    if (pos < POOL_CAP) pq[pos] = rbase + j;
+                                    ++pos;
                                 }
                             }
+                            __syncwarp();
+                        } else {
+                            // edge tile: warp-uniform loop over the (lane, column) hits; the column is re-read from
+                            // TMEM with a one-column load (no register indexing), the owning lane tests it exactly
+                            const float te = hq == 0 ? t_exact[0] : t_exact[1];
+                            const float* hc = h_part + c * 32;
+                            unsigned pend = __ballot_sync(0xffffffffu, m != 0);
+#pragma unroll 1
+                            while (pend) {
+                                const int src = __ffs(pend) - 1;
+                                const int j = __ffs(__shfl_sync(0xffffffffu, m, src)) - 1;        // warp-uniform column
+                                const uint32_t val = tmem_ld_32x1(taddr + c * 32 + j);
+                                tc_wait_ld();
+                                if (lane == src) {
+                                    scan_append(__uint_as_float(val), hc[j], te, row0 + c * 32 + j, ns32, &cnt_s[q], &lmax_s[q],
+                                                my_pool + q * POOL_CAP);
+                                    m &= m - 1;
+                                }
+                                pend = __ballot_sync(0xffffffffu, m != 0);
+                            }
                         }
-                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -505,8 +573,11 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             if (end) break;
             if (rf) apply_thresholds(tg, i);
-            if (i < 32 || (i & 3) == 0) publish_maxima();
-            if (i == 1) stamp(2);
+            if (i < warm + 32 || (i & 3) == 0) publish_maxima();
+            if (i == warm) stamp(2);
+            if (i == 16) stamp(5);
+            if (i == 32) stamp(6);
+            if (i == 96) stamp(7);
         }
         stamp(3);
         publish_maxima();
@@ -552,7 +623,13 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (lane == 0 && T > NEG_INF_ORD && T > ld_relaxed(&Tg[q])) st_relaxed(&Tg[q], T);
             }
             ++round;
-            __nanosleep(round < 48 ? 100 : (round < 96 ? 1000 : 4000));
+            // the select competes with four epilogue warps for its sub-partition's issue slots: once the first
+            // thresholds are out (a few rounds), one refresh every few tiles is as good as a continuous one
+            if ((tune & 1) || round < 6) {
+                __nanosleep((tune & 1) ? (round < 48 ? 100 : (round < 96 ? 1000 : 4000)) : 100);
+            } else {
+                for (int nap = 0; nap < 8 && smem_ld_volatile(&bars->done) < EPI_WARPS; ++nap) __nanosleep(500);   // prompt exit
+            }
         }
     }
 
@@ -953,6 +1030,14 @@ static int brute_rounds(nafp_index* idx, const float* q_dev, const int32_t* list
     return NAFP_OK;
 }
 
+// developer knob NAFP_SCAN_TUNE (A/B switches of flat_scan_kernel; every setting returns the same answers):
+// 1 = reducer polls continuously, 2 = one warm tile, 4 = exact per-column candidate path in every tile (the path
+// of tiles with halo / padding rows), 8 = thresholds re-read every tile during the first 32 tiles
+static int scan_tune() {
+    static const int v = [] { const char* e = getenv("NAFP_SCAN_TUNE"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_list, int src_off, int64_t p0, int np, int kg,
                      int grid_scan, int n_tiles, int64_t n_search, int slot) {
     nafp_ctx* ctx = idx->ctx;
@@ -972,7 +1057,7 @@ static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_lis
     if (prof) cudaEventRecord(idx->prof_ev[2 * idx->prof_n], ctx->stream);
     flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, idx->tile_counter, n_search,
                                                                           n_tiles, np, n_half, kg, idx->Mx, Tg, pool, cnt, flags,
-                                                                          idx->dbg_first);
+                                                                          idx->dbg_first, scan_tune());
     if (prof) {
         cudaEventRecord(idx->prof_ev[2 * idx->prof_n + 1], ctx->stream);
         idx->prof_n++;

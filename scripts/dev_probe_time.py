@@ -26,8 +26,8 @@ for rep in range(2):
     idx.search_dev(q.data_ptr(), nq, 20, D.data_ptr(), I.data_ptr()); torch.cuda.synchronize()
     cnt = np.zeros((G, 256), np.int32); first = np.zeros((G, 256), np.int32)
     check(lib.nafp_index_debug_enable(idx.h, ptr(cnt), ptr(first), None))
-    t = first[:, 248:253]
-    print("rep", rep, "G", G, "ns since start: tile0 done / thresholds ok / tile1 done / own tiles done / end")
+    t = first[:, 248:256]
+    print("rep", rep, "G", G, "ns since start: tile0 done / thresholds ok / first thresholded tile done / own tiles done / end / item 16 done / item 32 done / item 96 done")
     print(" median", np.median(t, 0).tolist(), " min", t.min(0).tolist(), " max", t.max(0).tolist())
     print(" survivors per CTA-query: mean", cnt[:, :nq].mean(), "max", cnt[:, :nq].max())
     own = t[:, 3]

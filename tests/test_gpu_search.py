@@ -175,3 +175,18 @@ def test_seq_match_matches_oracle(n_dummy):
     assert len(diff) <= 4
     assert np.abs(seq_match.hit_rates(raw_g, n_len) - seq_match.hit_rates(raw_o, n_len)).max() <= 0.1 + 100.0 * 2 / len(test_ids)
     np.testing.assert_array_equal(raw_g[:, :n_len], raw_o[:, :n_len]) if len(diff) == 0 else None
+
+
+@pytest.mark.parametrize("tune", ["6", "9"])
+def test_scan_variants_return_the_same_answers(tune):
+    """NAFP_SCAN_TUNE switches scan-kernel variants (4: the exact per-column candidate path of edge tiles in EVERY
+    tile, 2: a single warm tile, 1 / 8: the chattier threshold traffic): the fuzz against the fp64 oracle must pass
+    under each of them (the knob is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NAFP_SCAN_TUNE=tune)
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "dev_fuzz_search.py"), "3", "9"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
