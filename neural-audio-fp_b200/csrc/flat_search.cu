@@ -160,16 +160,34 @@ __device__ __forceinline__ void mbar_arrive_lane0(uint64_t* bar, int lane) {
         "r"(lane)
         : "memory");
 }
-// one survivor of the prefilter: exact bf16 score against the exact threshold, then the CTA's pool
-__device__ __forceinline__ void scan_append(float v, float h, float t_exact, uint32_t row, uint32_t n_search, int* cnt_q, int* lmax_q,
-                                         uint64_t* pool_q) {
-    if (row >= n_search) return;                 // halo / padding rows never score
-    const float s = v - h;
-    if (s > t_exact) {
-        const int so = f2ord(s);
-        const int pos = smem_atom_inc(cnt_q);
-        if (pos < POOL_CAP) pool_q[pos] = (static_cast<uint64_t>(static_cast<uint32_t>(so) ^ 0x80000000u) << 32) | row;
-        smem_red_max(lmax_q, so);
+// A chunk (32 accumulator columns = 32 DB rows) in which some lane's maximum passed the prefilter: every lane
+// tests its 32 scores exactly -- s = v - 0.5|x|^2 > T -- in straight-line code (bit mask of the hits, exact chunk
+// maximum); only then the lanes with hits diverge: one shared-memory add reserves their pool slots, the pool takes
+// the row ids (flat_select re-scores every survivor in fp32, the scan's score is not needed again), the running
+// maximum of the query takes the chunk maximum.  The first version inlined 32 predicated append bodies (14 KB of
+// branchy code); this one is ~150 instructions.  nvalid < 32 only in a tile that holds halo / padding rows.
+template <bool EDGE>
+__device__ __forceinline__ void scan_chunk_hits(const uint32_t (&v)[32], const float* __restrict__ hc, float t_exact, int nvalid,
+                                                uint32_t rbase, int* cnt_q, int* lmax_q, uint64_t* pool_q) {
+    uint32_t m = 0;
+    float best = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (!EDGE || j < nvalid) {
+            const float sj = __uint_as_float(v[j]) - hc[j];
+            m |= (sj > t_exact) ? (1u << j) : 0u;
+            best = fmaxf(best, sj);
+        }
+    }
+    if (m) {
+        smem_red_max(lmax_q, f2ord(best));
+        int pos = smem_atom_add(cnt_q, __popc(m));
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < POOL_CAP) pool_q[pos] = rbase + j;
+            ++pos;
+        }
     }
 }
 
@@ -410,16 +428,21 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int w = 0; w < warm; ++w) {
             const uint32_t row0 = static_cast<uint32_t>(cta + w * G) * SCAN_TILE + part * PART_COLS;
             const float* h_part = h_s + (w % H_RING) * SCAN_TILE + part * PART_COLS;
-            // a tile of searchable rows only: chunk maximum - max 0.5|x|^2 of the warp's 64 rows (a lower bound of
-            // the best score, exact for unit-norm rows); a tile with halo / padding rows: exact, column by column
-            const bool edge = (static_cast<uint32_t>(cta + w * G) + 1u) * SCAN_TILE > ns32 || (tune & 4);
+            // rows of (numerically) equal norm, all searchable -- fingerprints are unit vectors --: the best score of a
+            // chunk is its maximum minus the common 0.5|x|^2 (FMNMX3 chain).  Otherwise (reconstructions of an
+            // IVF-PQ index, raw vectors, halo / padding rows): exact, column by column.
+            bool edge = (static_cast<uint32_t>(cta + w * G) + 1u) * SCAN_TILE > ns32 || (tune & 4);
             float hx = 0.f;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
                 mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
-                if (hq == 0 && !edge)
-                    hx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(h_part[lane], h_part[32 + lane])))) *
-                         (1.f + 1.f / 1048576.f);
+                if (hq == 0 && !edge) {
+                    const float a = h_part[lane], b = h_part[32 + lane];
+                    const float hmax_w = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(a, b))));
+                    const float hmin_w = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(a, b))));
+                    hx = hmax_w * (1.f + 1.f / 1048576.f);
+                    edge = !(hmax_w - hmin_w <= hmax_w * (1.f / 262144.f));
+                }
                 tc_fence_after();
                 float munit = NEG_INF;
 #pragma unroll 1
@@ -477,7 +500,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (rf) load_thresholds(tg);
             const float* h_part = h_s + (i % H_RING) * SCAN_TILE + part * PART_COLS;
             uint32_t row0 = 0;
-            float hm = 0.f, hx = 0.f;
+            float hm = 0.f;
             bool end = false, edge = false;
             for (int hq = 0; hq < n_half; ++hq, ++uc) {
                 const int acc = uc & 1;
@@ -494,11 +517,7 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const float hmin_w =
                         __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(h_part[lane], h_part[32 + lane]))));
                     hm = hmin_w * (1.f - 1.f / 1048576.f);
-                    // largest 0.5|x|^2 of the same rows: v - hx is a lower bound of the score behind a chunk maximum v
-                    const float hmax_w =
-                        __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(h_part[lane], h_part[32 + lane]))));
-                    hx = hmax_w * (1.f + 1.f / 1048576.f);
-                    // the tile holds rows that do not take part in the search (halo, padding): exact per-column path
+                    // the tile holds rows that do not take part in the search (halo, padding)
                     edge = (static_cast<uint32_t>(tile) + 1u) * SCAN_TILE > ns32 || (tune & 4);
                 }
                 const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
@@ -522,49 +541,16 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const bool fired = ma > tp;
                     if (__any_sync(0xffffffffu, fired)) {
                         // rare -- except in the first thresholded tiles of a pass, while the thresholds are still
-                        // loose: the path must be SHORT (the first version inlined 32 predicated append bodies,
-                        // 14 KB of branchy code).  Bit mask of this lane's columns above its prefilter; the pool
-                        // only carries row ids (flat_select re-scores every survivor exactly), and the running
-                        // maximum takes the lower bound  chunk maximum - max 0.5|x|^2  -- a bound that is too
-                        // low or too high can only move the threshold, never the answer (flat_select proves it).
-                        uint32_t m = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > tp) ? (1u << j) : 0u;
+                        // loose (an event per warp per tile): see scan_chunk_hits
                         const int q = hq * 128 + qd * 32 + lane;
-                        if (!edge) {
-                            if (fired) {
-                                smem_red_max(&lmax_s[q], f2ord(ma - hx));
-                                int pos = smem_atom_add(&cnt_s[q], __popc(m));
-                                uint64_t* pq = my_pool + q * POOL_CAP;
-                                const uint32_t rbase = row0 + c * 32;
-                                while (m) {
-                                    const int j = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    if (pos < POOL_CAP) pq[pos] = rbase + j;
-                                    ++pos;
-                                }
-                            }
-                            __syncwarp();
-                        } else {
-                            // edge tile: warp-uniform loop over the (lane, column) hits; the column is re-read from
-                            // TMEM with a one-column load (no register indexing), the owning lane tests it exactly
-                            const float te = hq == 0 ? t_exact[0] : t_exact[1];
-                            const float* hc = h_part + c * 32;
-                            unsigned pend = __ballot_sync(0xffffffffu, m != 0);
-#pragma unroll 1
-                            while (pend) {
-                                const int src = __ffs(pend) - 1;
-                                const int j = __ffs(__shfl_sync(0xffffffffu, m, src)) - 1;        // warp-uniform column
-                                const uint32_t val = tmem_ld_32x1(taddr + c * 32 + j);
-                                tc_wait_ld();
-                                if (lane == src) {
-                                    scan_append(__uint_as_float(val), hc[j], te, row0 + c * 32 + j, ns32, &cnt_s[q], &lmax_s[q],
-                                                my_pool + q * POOL_CAP);
-                                    m &= m - 1;
-                                }
-                                pend = __ballot_sync(0xffffffffu, m != 0);
-                            }
-                        }
+                        const float te = hq == 0 ? t_exact[0] : t_exact[1];
+                        const uint32_t rbase = row0 + c * 32;
+                        if (!edge)
+                            scan_chunk_hits<false>(v, h_part + c * 32, te, 32, rbase, &cnt_s[q], &lmax_s[q], my_pool + q * POOL_CAP);
+                        else
+                            scan_chunk_hits<true>(v, h_part + c * 32, te, static_cast<int>(min(ns32 - min(ns32, rbase), 32u)), rbase,
+                                                  &cnt_s[q], &lmax_s[q], my_pool + q * POOL_CAP);
+                        __syncwarp();
                     }
                 }
                 tc_fence_before();
