@@ -334,9 +334,9 @@ def run_gpu(args):
     first, second = (tensor_part, hbm_part) if tensor_part["frac"] >= hbm_part["frac"] else (hbm_part, tensor_part)
     # DRAM bytes of ONE launch from the committed ncu --set full capture (same kernel, same 56,029,500-row
     # single-GPU shard, 256 query rows): dram__bytes_read.sum + dram__bytes_write.sum
-    traffic = 14.582701e9 + 8.297984e6 if rows_local == N_DUMMY_FULL + N_DB else None
+    traffic = 14.650915e9 + 7.794176e6 if rows_local == N_DUMMY_FULL + N_DB else None
     roofline = {"kernel": "flat_scan_kernel", **first, "traffic": traffic,
-                "traffic_source": "profiles/r1_prof_scan_final_summary.csv" if traffic else None,
+                "traffic_source": "profiles/r1_prof_scan_r1f_summary.csv" if traffic else None,
                 "other_bound": second, "launches": n_scans,
                 "avg_launch_ms": scan_avg_ms, "scan_share_of_step": scan_ms / max(ms_res * args.steps, 1e-9),
                 "query_rows_per_launch": q_rows_per_launch}
