@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(256)
 ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ coarse,
                   const float* __restrict__ pq, int m, int dsub, const int32_t* __restrict__ probes, int nprobe,
                   const uint8_t* __restrict__ lcodes, const int32_t* __restrict__ lids, const int32_t* __restrict__ loff,
-                  int k, int64_t label_offset, float* __restrict__ partD, int64_t* __restrict__ partI) {
+                  int k, int64_t label_offset, int64_t n_search, float* __restrict__ partD, int64_t* __restrict__ partI) {
     extern __shared__ float lut[];                          // [m][256]
     __shared__ uint64_t buf[IVF_SCAN_CAP];
     __shared__ int cnt_s;
@@ -401,7 +401,7 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
     __syncthreads();
     for (int64_t base = lo; base < hi; base += blockDim.x) {
         const int64_t pos = base + tid;
-        if (pos < hi) {
+        if (pos < hi && lids[pos] < n_search) {          // rows past n_search are the halo of a row-sharded index
             const uint4* cp = reinterpret_cast<const uint4*>(lcodes + pos * m);
             float d = 0.f;
             for (int v = 0; v < m / 16; ++v) {
@@ -447,7 +447,7 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
 __global__ void __launch_bounds__(256)
 ivfflat_scan_kernel(const float* __restrict__ q, int64_t nq, const int32_t* __restrict__ probes, int nprobe,
                     const float* __restrict__ x32, const int32_t* __restrict__ lids, const int32_t* __restrict__ loff,
-                    int k, int64_t label_offset, float* __restrict__ partD, int64_t* __restrict__ partI) {
+                    int k, int64_t label_offset, int64_t n_search, float* __restrict__ partD, int64_t* __restrict__ partI) {
     __shared__ uint64_t buf[IVF_SCAN_CAP];
     __shared__ int cnt_s;
     __shared__ unsigned long long thr_s;
@@ -471,8 +471,8 @@ ivfflat_scan_kernel(const float* __restrict__ q, int64_t nq, const int32_t* __re
 #pragma unroll 4
         for (int r = 0; r < ROWS_PER_WARP; ++r) {
             const int64_t pos = base + warp * ROWS_PER_WARP + r;
-            if (pos < hi) {
-                const int32_t row = lids[pos];
+            const int32_t row = pos < hi ? lids[pos] : INT_MAX;
+            if (row < n_search) {                        // (rows past n_search: halo of a row-sharded index)
                 const float4 xv = reinterpret_cast<const float4*>(x32 + static_cast<int64_t>(row) * D128)[lane];
                 const float d0 = qv.x - xv.x, d1 = qv.y - xv.y, d2 = qv.z - xv.z, d3 = qv.w - xv.w;
                 float d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
@@ -779,6 +779,7 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
     NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
                  "ivfpq search: need k <= %d and nprobe*k <= 2048 (nprobe %d, k %d)", MAX_K, nprobe, k);
     NAFP_TRY(build_lists(idx));
+    const int64_t n_search = (idx->search_rows >= 0 && idx->search_rows < idx->n) ? idx->search_rows : idx->n;
     const int64_t chunk = 4096;       // query rows per launch group (bounds the partial buffers)
     if (s->scratch_nq < std::min(nq, chunk) || s->scratch_nprobe < nprobe || s->scratch_k < k) {
         if (s->probes) cudaFree(s->probes);
@@ -802,11 +803,11 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
         ivfpq_probe_kernel<<<static_cast<unsigned>((nc + 7) / 8), 256, 0, ctx->stream>>>(qp, nc, s->coarse, s->nlist, nprobe, s->probes);
         if (s->flat_lists)
             ivfflat_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, 0, ctx->stream>>>(
-                qp, nc, s->probes, nprobe, idx->x32, s->lids, s->loff, k, idx->label_offset, s->partD, s->partI);
+                qp, nc, s->probes, nprobe, idx->x32, s->lids, s->loff, k, idx->label_offset, n_search, s->partD, s->partI);
         else
             ivfpq_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, lut_bytes, ctx->stream>>>(
                 qp, nc, s->coarse, s->pq, s->m, s->dsub, s->probes, nprobe, s->lcodes, s->lids, s->loff, k, idx->label_offset,
-                s->partD, s->partI);
+                n_search, s->partD, s->partI);
         topk_merge_kernel<<<static_cast<unsigned>(nc), 128, 0, ctx->stream>>>(s->partD, s->partI, nprobe, nc, k, D_dev + q0 * k,
                                                                               I_dev + q0 * k);
         ctx->launches += 3;

@@ -55,6 +55,11 @@ class TorchComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def broadcast(self, t, src=0):
+        """Quantizers of an IVF index trained on rank ``src`` (not on the search path)."""
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t
+
 
 def sharded_seq_match(ops, comm, query, test_ids, seq_lens, k_probe):
     """Backend-agnostic orchestration; see the module docstring.  ``query`` is the whole query set
@@ -156,19 +161,61 @@ class GpuOps:
 
 
 class ShardedFlatIndex:
-    """Rank-local block (+ halo) of a row-sharded flat index and the collective sequence matcher."""
+    """Rank-local block (+ halo) of a row-sharded index and the collective sequence matcher.
 
-    def __init__(self, n_rows_global, rank, world, max_len=19, device=None, comm=None):
-        from .eval.utils.get_index import FLAT_L2, Index
+    ``index_type`` FLAT_L2 (default), IVFPQ or IVF_FLAT (``eval/utils/get_index.py``).  The IVF types shard their
+    codes / lists by the same row blocks with the quantizers replicated (SURVEY §8 e, the equivalent of
+    faiss.IndexShards over one trained index): ``train`` runs on rank 0 and the centroids / codebooks are
+    broadcast, after which every rank adds its own rows."""
+
+    def __init__(self, n_rows_global, rank, world, max_len=19, device=None, comm=None, index_type=0, nlist=None,
+                 pq_m=64, pq_nbits=8):
+        from .eval.utils.get_index import FLAT_L2, IVF_FLAT, IVFPQ, Index
         self.rank, self.world = int(rank), int(world)
         self.n_rows_global = int(n_rows_global)
         self.max_len = int(max_len)
+        self.index_type = int(index_type)
         self.lo, self.hi, self.hi_halo = shard_with_halo(n_rows_global, rank, world, max_len - 1)
-        self.index = Index(FLAT_L2, 128, device=self.rank if device is None else device)
-        self.index.reserve(self.hi_halo - self.lo)
+        if nlist is None:
+            nlist = 400 if self.index_type == IVF_FLAT else 256          # get_index_faiss.py:65,71
+        self.index = Index(self.index_type, 128, nlist=nlist, pq_m=pq_m, pq_nbits=pq_nbits,
+                           device=self.rank if device is None else device)
+        self._ivf = self.index_type in (IVFPQ, IVF_FLAT)
+        self._ivfpq = self.index_type == IVFPQ
+        if not self._ivf:
+            self.index.reserve(self.hi_halo - self.lo)
         self.index.set_label_offset(self.lo)
         self.comm = comm
         self._ops = None
+
+    def train(self, x, seed=1234, nprobe=40):
+        """IVF types: k-means on rank 0, quantizers broadcast to the other ranks (no-op for the flat index)."""
+        if not self._ivf:
+            return
+        import torch
+        if self.rank == 0:
+            self.index.train(x, seed=seed)
+        if self.world > 1 or self.comm is not None and self.comm.world > 1:
+            dev = torch.device('cuda', self.index.ctx.device) if torch.cuda.is_available() else torch.device('cpu')
+            coarse = torch.empty((self.index.nlist, 128), dtype=torch.float32, device=dev)
+            pq = torch.empty((self.index.pq_m, 256, 128 // self.index.pq_m), dtype=torch.float32, device=dev) if self._ivfpq else None
+            if self.rank == 0:
+                if self._ivfpq:
+                    c, p = self.index.ivfpq_params()
+                    pq.copy_(torch.from_numpy(p))
+                else:
+                    c = self.index.ivf_coarse()
+                coarse.copy_(torch.from_numpy(c))
+            self.comm.broadcast(coarse, 0)
+            if self._ivfpq:
+                self.comm.broadcast(pq, 0)
+            if self.rank != 0:
+                if self._ivfpq:
+                    self.index.set_ivfpq_params(coarse.cpu().numpy(), pq.cpu().numpy())
+                else:
+                    self.index.set_ivf_coarse(coarse.cpu().numpy())
+        self.index.reserve(self.hi_halo - self.lo)
+        self.index.nprobe = nprobe
 
     @property
     def ntotal(self):
@@ -222,3 +269,6 @@ class ShardedFlatIndex:
         sl = torch.from_numpy(np.ascontiguousarray(seq_lens, dtype=np.int32)).to(dev, non_blocking=True)
         pid, psc = self.seq_match_dev(q, ids, sl, k_probe)
         return pid.cpu().numpy(), psc.cpu().numpy()
+
+
+ShardedIndex = ShardedFlatIndex      # the class serves every index type; the old name stays for its callers
