@@ -445,6 +445,30 @@ def run_gpu(args):
     ivf_full = None
     if world == 1 and args.ivfpq_full and n_dummy > 1_000_000:
         ivf_full = ivfpq_leg(n_dummy)
+    if world > 1 and args.ivfpq_full:
+        # BASELINE configs[4]: the IVF-PQ index row-sharded like the flat one (quantizers trained on rank 0 and
+        # broadcast, codes / lists / reconstructions local), same all-gather + merge + max all-reduce
+        from nafp_b200.eval.utils.get_index import IVFPQ
+        t_ivf = time.time()
+        sivf = ShardedFlatIndex(n_total, rank, world, max_len=max(SEQ_LENS), device=local_rank, comm=comm, index_type=IVFPQ)
+        tr = torch.empty((min(4_000_000, n_dummy), 128), dtype=torch.float32, device=dev)
+        check(lib.nafp_synth_fp_rows(ctx.h, 11, 0, tr.shape[0], 59, 0.5, ctypes.c_void_p(tr.data_ptr())))
+        sivf.train(tr[:: max(1, tr.shape[0] // 100_000)].contiguous().cpu().numpy())
+        del tr
+        t_train = time.time() - t_ivf
+        build_sharded_index(ctx, torch, sivf, n_dummy, dev)
+        t_add = time.time() - t_ivf - t_train
+
+        def sivf_step():
+            result["sivf"] = sivf.seq_match_dev(q_dev, ids_dev, sl_dev, K_PROBE)
+
+        ms_sivf = max_over_ranks(time_steps(torch, dev, sivf_step, args.steps, args.warmup, barrier))
+        sp = result["sivf"][0].cpu().numpy()
+        ivf_full = {"index": "IVFPQ nlist 256, M 64, 8 bit, nprobe 40, row-sharded", "db_rows": n_total,
+                    "value": n_queries / (ms_sivf * 1e-3), "unit": "queries/s", "ms_per_step": ms_sivf, "train_s": t_train,
+                    "add_s": t_add, "through": "device-resident queries (seq_match_dev), NCCL all-gather + max all-reduce",
+                    "top1_hit_rate": [float(100.0 * np.mean(sp[:, si, 0] == test_ids + n_dummy)) for si in range(len(SEQ_LENS))]}
+        del sivf
 
     # ---- CPU baseline (rank 0, N = 1): the oracle port on a bounded sample
     cpu = None
