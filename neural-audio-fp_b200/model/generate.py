@@ -32,6 +32,9 @@ def load_checkpoint(checkpoint_root_dir, checkpoint_name, checkpoint_index, m_fp
         print(f'---Initialised random weights (seed {seed})---')
         return 0 if checkpoint_index is None else checkpoint_index
     checkpoint_dir = checkpoint_root_dir + f'/{checkpoint_name}/'
+    # two on-disk forms: the .npz exchange file (model/weights.py) and the reference's own TensorFlow checkpoint
+    # (ckpt-N.index + ckpt-N.data-*), which model/tf_checkpoint.py reads without TensorFlow
+    from .tf_checkpoint import latest_checkpoint, load_tf_checkpoint
     if checkpoint_index is None:
         print("\x1b[1;32mArgument 'checkpoint_index' was not specified.\x1b[0m")
         print('\x1b[1;32mSearching for the latest checkpoint...\x1b[0m')
@@ -40,14 +43,21 @@ def load_checkpoint(checkpoint_root_dir, checkpoint_name, checkpoint_index, m_fp
             m = re.search(r'ckpt-(\d+)\.npz$', p)
             if m:
                 found.append(int(m.group(1)))
+        tf_index, _ = latest_checkpoint(checkpoint_dir)
+        if tf_index is not None:
+            found.append(tf_index)
         if not found:
             raise FileNotFoundError(f'Cannot find checkpoint in {checkpoint_dir}')
         checkpoint_index = max(found)
-    path = checkpoint_dir + 'ckpt-' + str(checkpoint_index) + '.npz'
-    if not os.path.exists(path):
-        raise FileNotFoundError(path)
-    m_fp.load(load_weights(path))
-    print(f'---Restored from {path}---')
+    prefix = checkpoint_dir + 'ckpt-' + str(checkpoint_index)
+    if os.path.exists(prefix + '.npz'):
+        m_fp.load(load_weights(prefix + '.npz'))
+        print(f'---Restored from {prefix}.npz---')
+    elif os.path.exists(prefix + '.index'):
+        m_fp.load(load_tf_checkpoint(prefix))
+        print(f'---Restored from {prefix} (TensorFlow checkpoint)---')
+    else:
+        raise FileNotFoundError(prefix + '.npz / .index')
     return checkpoint_index
 
 
