@@ -87,3 +87,23 @@ def test_product_cli_ivfpq_runs_the_same_job(tmp_path, ref_eval):
     top1, top1_flat = 100.0 * raw[:, :6].mean(0), 100.0 * ref_eval["raw_score"][:, :6].mean(0)
     assert (top1 <= top1_flat + 3.0).all() and (top1 >= top1_flat - 20.0).all(), (top1, top1_flat)
     assert top1[-1] >= 97.0
+
+
+@pytest.mark.gpu
+def test_product_cli_ivf_runs_the_same_job(tmp_path, ref_eval):
+    """index_type 'ivf' (IndexIVFFlat, nlist 400, nprobe 40) through the evaluate entry point.  Exact distances, but
+    only a tenth of the lists is probed, and the fixture's fingerprints are nearly unclustered random unit vectors:
+    short queries lose up to 27 points against the exact index (measured 22 / 52 / 66 / 82 / 87 / 96 % vs
+    29 / 79 / 90 / 98.5 / 98.5 / 100 %); id-for-id parity with the oracle is tests/test_gpu_ivfpq.py's job."""
+    from nafp_b200.eval.eval_search import run_eval
+    emb = str(tmp_path) + "/"
+    gold.write_emb_dir(emb)
+    ids_path = os.path.join(emb, "ids.npy")
+    np.save(ids_path, np.asarray(gold.EVAL["test_ids"], np.int64))
+    run_eval(emb, None, 'ivf', False, 1e7, ids_path, gold.EVAL["seq_lens"], gold.EVAL["k_probe"], 5)
+    raw = np.load(emb + "raw_score.npy")
+    assert raw.shape == ref_eval["raw_score"].shape
+    np.testing.assert_array_equal(np.load(emb + "test_ids.npy"), ref_eval["test_ids"])
+    top1, top1_flat = 100.0 * raw[:, :6].mean(0), 100.0 * ref_eval["raw_score"][:, :6].mean(0)
+    assert (top1 <= top1_flat + 3.0).all() and (top1 >= top1_flat - 35.0).all(), (top1, top1_flat)
+    assert top1[-1] >= 90.0 and (np.diff(top1) > 0).all()
