@@ -264,7 +264,10 @@ class ShardedFlatIndex:
         """Host arrays in, host arrays out (includes H2D / D2H)."""
         import torch
         dev = torch.device('cuda', self.index.ctx.device)
-        q = torch.from_numpy(np.ascontiguousarray(query, dtype=np.float32)).to(dev, non_blocking=True)
+        query = np.ascontiguousarray(query, dtype=np.float32)
+        if not query.flags.writeable:          # read-only memmaps: torch wants a writable buffer
+            query = query.copy()
+        q = torch.from_numpy(query).to(dev, non_blocking=True)
         ids = torch.from_numpy(np.ascontiguousarray(test_ids, dtype=np.int64)).to(dev, non_blocking=True)
         sl = torch.from_numpy(np.ascontiguousarray(seq_lens, dtype=np.int32)).to(dev, non_blocking=True)
         pid, psc = self.seq_match_dev(q, ids, sl, k_probe)

@@ -8,6 +8,10 @@ serves every shorter one; offset compensation, unique candidates, sequence score
 CUDA kernels).  Deliberate deviations, both listed in DESIGN.md: ``dummy_db.mm`` is NOT extended on
 disk (the reference's ``fake_recon_index``, ``:167-171``; the device index already holds [dummy; db]),
 and ``--nogpu`` is refused (there is no CPU search path).
+
+Multi-GPU: started under ``torchrun`` (WORLD_SIZE > 1) the database is row-sharded over the ranks
+(``nafp_b200.dist.ShardedFlatIndex``: every rank reads only its block of the memmaps; per-rank top-k merged by an
+NCCL all-gather, candidate scores by a max all-reduce); rank 0 prints the table and writes the outputs.
 """
 from __future__ import annotations
 
@@ -59,9 +63,48 @@ def select_test_ids(test_ids, n_query, test_seq_len, rng=None):
     return np.load(test_ids)
 
 
+def _sharded_index(index_type, dummy_db, db, max_len, max_train, rank, world, device):
+    """Row-sharded stand-in for ``get_index`` + the two ``index.add`` calls (``eval_faiss.py:141-151``)."""
+    from ..dist import ShardedFlatIndex, TorchComm
+    from .utils.get_index import FLAT_L2, IVF_FLAT, IVFPQ
+    kinds = {'l2': FLAT_L2, 'ivfpq': IVFPQ, 'ivf': IVF_FLAT}
+    mode = index_type.lower()
+    if mode not in kinds:
+        raise NotImplementedError(f"index_type '{mode}' is not built (l2, ivfpq, ivf)")
+    comm = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            torch.cuda.set_device(device)
+            dist.init_process_group('nccl')
+        comm = TorchComm()
+    print(f'Creating index: \033[93m{mode}\033[0m (rank {rank} of {world}, rows sharded)')
+    index = ShardedFlatIndex(len(dummy_db) + len(db), rank, world, max_len=max_len, device=device, comm=comm,
+                             index_type=kinds[mode])
+    if mode != 'l2':
+        start_time = time.time()
+        max_train = int(max_train)
+        train = dummy_db
+        if rank == 0 and len(dummy_db) > max_train:     # eval_faiss.py:107-113 (only rank 0 trains)
+            sel = np.sort(np.random.default_rng(None).permutation(len(dummy_db))[:max_train])
+            train = dummy_db[sel, :]
+        index.train(train if rank == 0 else None)
+        print('Elapsed time: {:.2f} seconds.'.format(time.time() - start_time))
+    index.add_from([dummy_db, db])
+    return index
+
+
 def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_train=1e7, test_ids='icassp',
-             test_seq_len='1 3 5 9 11 19', k_probe=20, display_interval=5, device=0, live=None):
+             test_seq_len='1 3 5 9 11 19', k_probe=20, display_interval=5, device=0, live=None, sharded=None):
     test_seq_len = np.asarray(list(map(int, test_seq_len.split())))
+    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    if sharded is None:
+        sharded = world > 1
+    if not sharded:
+        world, rank = 1, 0
+    elif world > 1:
+        device = int(os.environ.get('LOCAL_RANK', str(rank)))
 
     query, query_shape = load_memmap_data(emb_dir, 'query')
     db, db_shape = load_memmap_data(emb_dir, 'db')
@@ -69,16 +112,27 @@ def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_t
         emb_dummy_dir = emb_dir
     dummy_db, dummy_db_shape = load_memmap_data(emb_dummy_dir, 'dummy_db')
 
-    index = get_index(index_type, dummy_db, dummy_db.shape, (not nogpu), max_train, device=device)
-
-    start_time = time.time()
-    index.add(dummy_db); print(f'{len(dummy_db)} items from dummy DB')
-    index.add(db); print(f'{len(db)} items from reference DB')
+    if sharded:
+        if nogpu:
+            from .._lib import NafpError
+            raise NafpError("--nogpu: nafp-b200 has no CPU search path (no fallback by design)")
+        start_time = time.time()
+        index = _sharded_index(index_type, dummy_db, db, int(max(test_seq_len)), max_train, rank, world, device)
+    else:
+        index = get_index(index_type, dummy_db, dummy_db.shape, (not nogpu), max_train, device=device)
+        start_time = time.time()
+        index.add(dummy_db); print(f'{len(dummy_db)} items from dummy DB')
+        index.add(db); print(f'{len(db)} items from reference DB')
     t = time.time() - start_time
     print(f'Added total {index.ntotal} items to DB. {t:>4.2f} sec.')
 
     print(f'test_id: \033[93m{test_ids}\033[0m,  ', end='')
     test_ids = np.asarray(select_test_ids(test_ids, len(query), test_seq_len), dtype=np.int64)
+    if sharded and world > 1:          # a random selection ('N' test ids) must be the same on every rank
+        import torch
+        t_ids = torch.from_numpy(test_ids).to(torch.device('cuda', device))
+        index.comm.broadcast(t_ids, 0)
+        test_ids = t_ids.cpu().numpy()
     n_test = len(test_ids)
     gt_ids = test_ids + dummy_db_shape[0]
     print(f'n_test: \033[93m{n_test:n}\033[0m')
@@ -90,7 +144,7 @@ def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_t
     top10_exact = np.zeros((n_test, n_len)).astype(int)
 
     pt = PrintTable(test_seq_len=test_seq_len,
-                    row_names=['Top1 exact', 'Top1 near', 'Top3 exact', 'Top10 exact'], live=live)
+                    row_names=['Top1 exact', 'Top1 near', 'Top3 exact', 'Top10 exact'], live=live if rank == 0 else False)
     query_np = np.ascontiguousarray(query)
     # ids are processed in blocks; a block is one batched GPU call (the reference refreshes its table
     # every display_interval ids -- blocks are a multiple of that so the refresh points coincide)
@@ -109,16 +163,18 @@ def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_t
         done = b0 + len(ids)
         avg_search_time = (time.time() - start_time) / len(ids) / n_len
         rates = tuple(100. * np.mean(a[:done, :], axis=0) for a in (top1_exact, top1_near, top3_exact, top10_exact))
-        pt.update_counter(done - 1, n_test, avg_search_time * 1000.)
-        pt.update_table(rates)
+        if rank == 0:
+            pt.update_counter(done - 1, n_test, avg_search_time * 1000.)
+            pt.update_table(rates)
 
     rates = tuple(100. * np.mean(a, axis=0) for a in (top1_exact, top1_near, top3_exact, top10_exact))
-    pt.update_counter(n_test - 1, n_test, avg_search_time * 1000.)
-    pt.update_table(rates)
-    pt.close_table()
-    np.save(f'{emb_dir}/raw_score.npy', np.concatenate((top1_exact, top1_near, top3_exact, top10_exact), axis=1))
-    np.save(f'{emb_dir}/test_ids.npy', test_ids)
-    print(f'Saved test_ids and raw score to {emb_dir}.')
+    if rank == 0:
+        pt.update_counter(n_test - 1, n_test, avg_search_time * 1000.)
+        pt.update_table(rates)
+        pt.close_table()
+        np.save(f'{emb_dir}/raw_score.npy', np.concatenate((top1_exact, top1_near, top3_exact, top10_exact), axis=1))
+        np.save(f'{emb_dir}/test_ids.npy', test_ids)
+        print(f'Saved test_ids and raw score to {emb_dir}.')
     return rates
 
 

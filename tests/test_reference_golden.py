@@ -107,3 +107,17 @@ def test_product_cli_ivf_runs_the_same_job(tmp_path, ref_eval):
     top1, top1_flat = 100.0 * raw[:, :6].mean(0), 100.0 * ref_eval["raw_score"][:, :6].mean(0)
     assert (top1 <= top1_flat + 3.0).all() and (top1 >= top1_flat - 35.0).all(), (top1, top1_flat)
     assert top1[-1] >= 90.0 and (np.diff(top1) > 0).all()
+
+
+@pytest.mark.gpu
+def test_product_cli_row_sharded_path_reproduces_reference_eval_loop(tmp_path, ref_eval):
+    """The torchrun (row-sharded) form of the evaluate entry point, here with a single rank: same raw_score.npy as
+    the reference's own loop."""
+    from nafp_b200.eval.eval_search import run_eval
+    emb = str(tmp_path) + "/"
+    gold.write_emb_dir(emb)
+    ids_path = os.path.join(emb, "ids.npy")
+    np.save(ids_path, np.asarray(gold.EVAL["test_ids"], np.int64))
+    run_eval(emb, None, 'l2', False, 1e7, ids_path, gold.EVAL["seq_lens"], gold.EVAL["k_probe"], 5, sharded=True)
+    np.testing.assert_array_equal(np.load(emb + "raw_score.npy"), ref_eval["raw_score"])
+    np.testing.assert_array_equal(np.load(emb + "test_ids.npy"), ref_eval["test_ids"])
