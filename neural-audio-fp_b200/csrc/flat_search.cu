@@ -7,15 +7,18 @@
 //
 // One scan pass handles up to 256 query rows against the whole database:
 //   flat_prep_kernel    fp32 queries -> bf16 A-operand tile, |q|^2, pass state reset
-//   flat_scan_kernel    persistent, one CTA per SM, each CTA owns a contiguous run of 256-row DB
-//                       tiles: TMA (SWIZZLE_128B) -> smem ring of K blocks -> tcgen05.mma (M = 128
+//   flat_scan_kernel    persistent, one CTA per SM, 256-row DB tiles handed out by a global counter:
+//                       TMA (SWIZZLE_128B) -> smem ring of K blocks -> tcgen05.mma (M = 128
 //                       queries, N = 256 DB rows, K = 128, bf16, fp32 accumulators double-buffered in
 //                       TMEM) -> epilogue threads own one query each: a 3-input max over the tile's
-//                       columns and ONE compare against  T + min_tile 0.5|x|^2 ; the rare columns
-//                       that pass get the exact  q.x - 0.5|x|^2 > T  test and join the CTA's pool.
+//                       columns and ONE compare against  T + min_tile 0.5|x|^2 ; a 32-column chunk in
+//                       which a lane fires gets the exact  q.x - 0.5|x|^2 > T  test in straight-line
+//                       code and its hits' row ids join the CTA's pool.
 //                       T is a per-query threshold that all CTAs share through L2 (the kg-th largest
 //                       of the per-CTA running maxima -- a valid lower bound on the kg-th best
-//                       score, maintained by one reducer warp per CTA, lock-free).
+//                       score, maintained by one reducer warp per CTA, lock-free); every CTA first scans
+//                       eight "warm" tiles max-only (re-visited at the end) so that the thresholds are
+//                       tight before the first candidate is appended.
 //   flat_select_kernel  per query: gather survivors, exact fp32 re-score, sort, and PROVE the
 //                       top-k: every dropped row has bf16 score <= T, hence exact score <= T + eps
 //                       with eps = (2u+u^2)|q|max|x| (u = 2^-8); if the k-th exact score is not
@@ -23,10 +26,9 @@
 //   flat_brute_*        exact fp32 CUDA-core scan for flagged queries / tiny databases.
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
-
-#include <cstdlib>
 
 #include "index.h"
 #include "ptx.cuh"
