@@ -115,6 +115,13 @@ int nafp_fingerprint_host(nafp_ctx* ctx, const float* x_host, int64_t n_seg, int
  * the device; pcm_host is (n_seg, 8000) int16. */
 int nafp_fingerprint_pcm16_host(nafp_ctx* ctx, const int16_t* pcm_host, int64_t n_seg,
                                 int64_t group_size, float* emb_host);
+/* The same for whole-track sample runs: pcm_host holds n_samples int16 samples (tracks back to back); segment s is
+ * the window [seg_off[s], seg_off[s] + 8000) of it, of which the first seg_valid[s] (<= 8000) samples are real and
+ * the rest is zero padding (get_fns_seg_list / load_audio, model/utils/audio_utils.py:140-264, with the 0.5 s hop
+ * applied on the device: overlapping segments are uploaded once). */
+int nafp_fingerprint_pcm16_tracks_host(nafp_ctx* ctx, const int16_t* pcm_host, int64_t n_samples,
+                                       const int64_t* seg_off_host, const int32_t* seg_valid_host,
+                                       int64_t n_seg, int64_t group_size, float* emb_host);
 /* Debug/parity taps: post-LayerNorm activation of conv `layer` (0..15) for the LAST
  * nafp_encoder_forward call, as float32 (n_seg, F, T, C) into out_host. */
 int nafp_encoder_activation_host(nafp_ctx* ctx, int layer, int64_t n_seg, float* out_host);

@@ -27,7 +27,7 @@
 namespace nafp {
 
 int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int64_t group_size, float* mel_dev,
-               bool finish, const int32_t** gmax_out);
+               bool finish, const int32_t** gmax_out, const int64_t* seg_off, const int32_t* seg_valid);
 
 constexpr int ENC_LAYERS = 16;
 constexpr int ENC_CHUNK_MAX = 4000;    // most segments of one encoder pass (2.3 MB of activations each): at 1,000 the
@@ -817,7 +817,7 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
 }
 
 static int fingerprint_dev(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int64_t group_size,
-                           float* emb_dev) {
+                           float* emb_dev, const int64_t* seg_off = nullptr, const int32_t* seg_valid = nullptr) {
     EncoderState* s = ctx->encoder;
     // chunks are whole groups so that every group's batch-global max is complete (melspectrogram.py:108)
     int64_t chunk = group_size <= ENC_CHUNK_MAX ? (ENC_CHUNK_MAX / group_size) * group_size : 0;
@@ -828,8 +828,10 @@ static int fingerprint_dev(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t
     for (int64_t s0 = 0; s0 < n_seg; s0 += chunk) {
         const int n = static_cast<int>(n_seg - s0 < chunk ? n_seg - s0 : chunk);
         const int32_t* gmax = nullptr;
-        const void* xin = static_cast<const uint8_t*>(x_dev) + static_cast<size_t>(s0) * 8000 * elt;
-        NAFP_TRY(logmel_run(ctx, xin, pcm16, n, group_size, s->mel, false, &gmax));
+        // (n_seg, 8000) rows, or windows of track sample runs addressed through seg_off (absolute sample offsets)
+        const void* xin = seg_off ? x_dev : static_cast<const uint8_t*>(x_dev) + static_cast<size_t>(s0) * 8000 * elt;
+        NAFP_TRY(logmel_run(ctx, xin, pcm16, n, group_size, s->mel, false, &gmax, seg_off ? seg_off + s0 : nullptr,
+                            seg_valid ? seg_valid + s0 : nullptr));
         NAFP_TRY(encoder_pass(ctx, s->mel, gmax, group_size, 0, n, emb_dev + s0 * EMB));
     }
     return NAFP_OK;
@@ -954,6 +956,44 @@ int nafp_fingerprint_host(nafp_ctx* ctx, const float* x_host, int64_t n_seg, int
 int nafp_fingerprint_pcm16_host(nafp_ctx* ctx, const int16_t* pcm_host, int64_t n_seg, int64_t group_size,
                                 float* emb_host) {
     return fingerprint_host(ctx, pcm_host, true, n_seg, group_size, emb_host);
+}
+
+// generate.py's path: whole-track int16 sample runs + one (offset, valid length) pair per segment; the overlapping
+// 1 s segments (0.5 s hop) are cut by the log-mel kernel, so every sample is uploaded once instead of twice and the
+// host never materialises the (n_seg, 8000) array.
+int nafp_fingerprint_pcm16_tracks_host(nafp_ctx* ctx, const int16_t* pcm_host, int64_t n_samples, const int64_t* seg_off_host,
+                                       const int32_t* seg_valid_host, int64_t n_seg, int64_t group_size, float* emb_host) {
+    NAFP_REQUIRE(ctx && n_seg >= 0 && n_samples >= 0 && group_size >= 1 &&
+                     (n_seg == 0 || (pcm_host && seg_off_host && seg_valid_host && emb_host)),
+                 NAFP_ERR_INVALID, "nafp_fingerprint_pcm16_tracks_host: bad arguments");
+    NAFP_REQUIRE(ctx->encoder && ctx->encoder->weights, NAFP_ERR_STATE,
+                 "nafp_fingerprint_pcm16_tracks_host: call nafp_weights_load first");
+    if (n_seg == 0) return NAFP_OK;
+    for (int64_t i = 0; i < n_seg; ++i)
+        NAFP_REQUIRE(seg_off_host[i] >= 0 && seg_valid_host[i] >= 0 && seg_valid_host[i] <= 8000 &&
+                         seg_off_host[i] + seg_valid_host[i] <= n_samples,
+                     NAFP_ERR_INVALID, "nafp_fingerprint_pcm16_tracks_host: segment %lld reads [%lld, +%d) of %lld samples",
+                     (long long)i, (long long)seg_off_host[i], (int)seg_valid_host[i], (long long)n_samples);
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));      // the staging buffer may be re-allocated below
+    // one staging buffer, every part 256-byte aligned: samples (+1 so that it is never empty), offsets, valid
+    // lengths, fingerprints
+    const int64_t pcm_bytes = (n_samples + 1) * 2, pcm_pad = (pcm_bytes + 255) / 256 * 256;
+    const int64_t off_bytes = (n_seg * 8 + 255) / 256 * 256, val_bytes = (n_seg * 4 + 255) / 256 * 256;
+    const int64_t emb_bytes = n_seg * EMB * static_cast<int64_t>(sizeof(float));
+    NAFP_TRY(ensure_dev(ctx, &ctx->stage_dev, &ctx->stage_dev_bytes, pcm_pad + off_bytes + val_bytes + emb_bytes));
+    uint8_t* base = static_cast<uint8_t*>(ctx->stage_dev);
+    int16_t* pcm_dev = reinterpret_cast<int16_t*>(base);
+    int64_t* off_dev = reinterpret_cast<int64_t*>(base + pcm_pad);
+    int32_t* val_dev = reinterpret_cast<int32_t*>(base + pcm_pad + off_bytes);
+    float* emb_dev = reinterpret_cast<float*>(base + pcm_pad + off_bytes + val_bytes);
+    NAFP_CUDA(cudaMemcpyAsync(pcm_dev, pcm_host, static_cast<size_t>(n_samples) * 2, cudaMemcpyHostToDevice, ctx->stream));
+    NAFP_CUDA(cudaMemcpyAsync(off_dev, seg_off_host, static_cast<size_t>(n_seg) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    NAFP_CUDA(cudaMemcpyAsync(val_dev, seg_valid_host, static_cast<size_t>(n_seg) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NAFP_TRY(fingerprint_dev(ctx, pcm_dev, true, n_seg, group_size, emb_dev, off_dev, val_dev));
+    NAFP_CUDA(cudaMemcpyAsync(emb_host, emb_dev, static_cast<size_t>(emb_bytes), cudaMemcpyDeviceToHost, ctx->stream));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NAFP_OK;
 }
 
 int nafp_encoder_activation_host(nafp_ctx* ctx, int layer, int64_t n_seg, float* out_host) {

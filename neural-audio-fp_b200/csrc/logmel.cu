@@ -85,7 +85,8 @@ __device__ __forceinline__ float to_sample<int16_t>(int16_t v) { return static_c
 template <typename TIn>
 __global__ void __launch_bounds__(256, 2)
 logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, const float* __restrict__ melw,
-              const int* __restrict__ start, float* __restrict__ out, int32_t* __restrict__ gmax) {
+              const int* __restrict__ start, float* __restrict__ out, int32_t* __restrict__ gmax,
+              const int64_t* __restrict__ seg_off, const int32_t* __restrict__ seg_valid) {
     extern __shared__ float smem[];
     float* xs = smem;                                  // [PADDED]
     float* grp = xs + PADDED;                          // 4 x GRP_FLOATS
@@ -97,11 +98,15 @@ logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, cons
     const int g = tid >> 6;          // frame group 0..3
     const int t = tid & 63;          // thread in group
 
-    // stage the segment, zero padded
-    const TIn* xin = x + seg * SEG_LEN;
+    // stage the segment, zero padded.  Segments are either rows of an (n_seg, 8000) array or -- seg_off != NULL --
+    // windows of whole-track sample runs (segment s starts at sample seg_off[s] and has seg_valid[s] <= 8000 real
+    // samples, the rest is the zero padding of audio_utils.py:249-252): overlapping segments are cut on the GPU
+    // and every sample crosses PCIe once.
+    const TIn* xin = x + (seg_off ? seg_off[seg] : seg * SEG_LEN);
+    const int n_valid = seg_valid ? seg_valid[seg] : SEG_LEN;
     for (int i = tid; i < PADDED; i += 256) {
         const int s = i - PAD;
-        xs[i] = (s >= 0 && s < SEG_LEN) ? to_sample<TIn>(xin[s]) : 0.f;
+        xs[i] = (s >= 0 && s < n_valid) ? to_sample<TIn>(xin[s]) : 0.f;
     }
 
     // per-thread constants
@@ -305,7 +310,7 @@ void logmel_destroy(nafp_ctx* ctx) {
 // raw (un-normalised) log-mel + per-group maxima; `finish` applies the max subtraction and clamp.
 // Returns the device pointer of the group maxima through gmax_out (valid until the next call).
 int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int64_t group_size, float* mel_dev,
-               bool finish, const int32_t** gmax_out) {
+               bool finish, const int32_t** gmax_out, const int64_t* seg_off, const int32_t* seg_valid) {
     NAFP_REQUIRE(ctx && (n_seg == 0 || (x_dev && mel_dev)) && n_seg >= 0 && group_size >= 1, NAFP_ERR_INVALID,
                  "logmel: bad arguments (n_seg=%lld group_size=%lld)", (long long)n_seg, (long long)group_size);
     NAFP_CUDA(cudaSetDevice(ctx->device));
@@ -324,10 +329,10 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
         s->gmax, groups, static_cast<int32_t>(0x807FFFFFu));
     if (pcm16)
         logmel_kernel<int16_t><<<static_cast<unsigned>(n_seg), 256, LOGMEL_SMEM, ctx->stream>>>(
-            static_cast<const int16_t*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax);
+            static_cast<const int16_t*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, seg_off, seg_valid);
     else
         logmel_kernel<float><<<static_cast<unsigned>(n_seg), 256, LOGMEL_SMEM, ctx->stream>>>(
-            static_cast<const float*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax);
+            static_cast<const float*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, seg_off, seg_valid);
     ctx->launches += 2;
     if (finish) {
         const int64_t n4 = n_seg * (NMEL * NFRAMES / 4);
@@ -345,5 +350,5 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
 extern "C" int nafp_logmel_forward(nafp_ctx* ctx, const float* x_dev, int64_t n_seg, int64_t group_size,
                                    float* mel_dev) {
     NAFP_REQUIRE(ctx, NAFP_ERR_INVALID, "nafp_logmel_forward: ctx is NULL");
-    return nafp::logmel_run(ctx, x_dev, false, n_seg, group_size, mel_dev, true, nullptr);
+    return nafp::logmel_run(ctx, x_dev, false, n_seg, group_size, mel_dev, true, nullptr, nullptr, nullptr);
 }

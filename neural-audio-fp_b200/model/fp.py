@@ -129,6 +129,22 @@ class FingerPrinter:
         check(fn(self.ctx.h, ptr(x), n, int(group_size), ptr(emb)))
         return emb
 
+    def fingerprint_tracks(self, pcm, seg_off, seg_valid, group_size):
+        """``fingerprint`` for segments given as windows of whole-track int16 sample runs
+        (``SegmentSequence.get_track_block``): the overlapping segments are cut on the GPU."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        seg_valid = np.ascontiguousarray(seg_valid, dtype=np.int32)
+        n = len(seg_off)
+        if len(seg_valid) != n:
+            raise ValueError("seg_off and seg_valid differ in length")
+        emb = np.empty((n, 128), dtype=np.float32)
+        if n == 0:
+            return emb
+        check(lib.nafp_fingerprint_pcm16_tracks_host(self.ctx.h, ptr(pcm), len(pcm), ptr(seg_off), ptr(seg_valid), n,
+                                                     int(group_size), ptr(emb)))
+        return emb
+
     def activation(self, layer, n_seg):
         """Post-LayerNorm activation (n_seg, F, T, C) of conv ``layer`` from the last encoder pass."""
         s = arch.conv_specs()[layer]

@@ -130,16 +130,20 @@ def generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source_root_dir
 
         print(f"=== Generating fingerprint from \x1b[1;32m'{key}'\x1b[0m bsz={bsz}, {n_items} items, d={dim} ===")
         b_lo, b_hi = _shard(len(ds[key]), rank, world_size)
-        i = b_lo
-        while i < b_hi:
-            j = min(i + batches_per_call, b_hi)
-            # several whole batches per call; the library keeps TS_BATCH_SZ groups separate
-            pcm = np.concatenate([ds[key].get_pcm(b) for b in range(i, j)], axis=0)
-            emb = m_fp.fingerprint(pcm, group_size=bsz)
-            arr[i * bsz:i * bsz + len(emb), :] = emb
-            i = j
-            if rank == 0:
-                print(f'\r{i - b_lo}/{b_hi - b_lo}', end='', flush=True)
+        # several whole batches per call (the library keeps TS_BATCH_SZ groups separate); the next block is cut
+        # from the WAV files by a worker thread while the GPU works on this one (ctypes releases the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        blocks = [(i, min(i + batches_per_call, b_hi)) for i in range(b_lo, b_hi, batches_per_call)]
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            nxt = pool.submit(ds[key].get_track_block, *blocks[0]) if blocks else None
+            for n_blk, (i, j) in enumerate(blocks):
+                pcm, seg_off, seg_valid = nxt.result()
+                nxt = pool.submit(ds[key].get_track_block, *blocks[n_blk + 1]) if n_blk + 1 < len(blocks) else None
+                # whole-track sample runs + one window per segment: the GPU cuts the overlapping segments
+                emb = m_fp.fingerprint_tracks(pcm, seg_off, seg_valid, group_size=bsz)
+                arr[i * bsz:i * bsz + len(emb), :] = emb
+                if rank == 0:
+                    print(f'\r{j - b_lo}/{b_hi - b_lo}', end='', flush=True)
         if rank == 0:
             print()
         print(f'=== Succesfully stored {arr_shape[0]} fingerprint to {output_root_dir} ===')

@@ -105,3 +105,26 @@ def test_encoder_requires_weights(ctx):
     fresh = Context(0)                 # a context that never saw nafp_weights_load
     with pytest.raises(NafpError):
         FingerPrinter(fresh)(np.zeros((1, 256, 32, 1), np.float32))
+
+
+def test_track_windows_cut_on_the_gpu_equal_host_cut_segments(tmp_path):
+    """nafp_fingerprint_pcm16_tracks_host (whole-track sample runs + one window per segment, what generate.py sends)
+    returns bit for bit the fingerprints of the host-cut (n_seg, 8000) int16 rows -- short file (zero padding),
+    file boundaries inside a group, partial last group."""
+    from nafp_b200 import synth
+    from nafp_b200._lib import Context
+    from nafp_b200.model import dataset, fp as FP, weights as W
+    paths = []
+    for i, n in enumerate([30000, 8000, 5000, 44123, 240000]):
+        p = str(tmp_path / f"t{i}.wav")
+        synth.write_wav(p, synth.synth_track(i, n_samples=n))
+        paths.append(p)
+    seq = dataset.SegmentSequence(paths, bsz=7)
+    m_fp = FP.FingerPrinter(Context.get(0)).load(W.init_weights(7, randomize_affine=True))
+    rows = seq.get_pcm_range(0, len(seq))
+    ref = m_fp.fingerprint(rows, group_size=7)
+    pcm, off, valid = seq.get_track_block(0, len(seq))
+    got = m_fp.fingerprint_tracks(pcm, off, valid, group_size=7)
+    assert got.shape == ref.shape == (seq.n_samples, 128)
+    np.testing.assert_array_equal(got, ref)
+    assert len(pcm) < 0.6 * rows.size

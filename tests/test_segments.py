@@ -47,3 +47,37 @@ def test_wrong_sample_rate_rejected(tmp_path):
     synth.write_wav(p, synth.synth_track(0, 9000), fs=16000)
     with pytest.raises(ValueError):
         dataset.SegmentSequence([p])
+
+
+def test_strided_range_cut_equals_per_segment_cut(wavs):
+    """get_pcm_range (one strided copy per file, what generate.py hands to the GPU) == the concatenation of the
+    per-segment batches, for every range of batches, across file boundaries, short files and the partial last batch."""
+    for bsz in (1, 3, 4, 7, 125):
+        seq = dataset.SegmentSequence(wavs, bsz=bsz)
+        per_batch = [seq.get_pcm(b) for b in range(len(seq))]
+        for lo in range(len(seq)):
+            for hi in range(lo + 1, len(seq) + 1):
+                np.testing.assert_array_equal(seq.get_pcm_range(lo, hi), np.concatenate(per_batch[lo:hi], axis=0))
+    with pytest.raises(IndexError):
+        dataset.SegmentSequence(wavs, bsz=4).get_pcm_range(5, 6)
+
+
+def test_track_block_windows_equal_the_cut_segments(wavs):
+    """get_track_block (what generate.py uploads: sample runs + one window per segment) describes exactly the rows
+    of get_pcm_range: window [off, off + valid) of the run, zero padded to one segment."""
+    for bsz in (1, 4, 7, 125):
+        seq = dataset.SegmentSequence(wavs, bsz=bsz)
+        for lo in range(len(seq)):
+            for hi in range(lo + 1, len(seq) + 1):
+                pcm, off, valid = seq.get_track_block(lo, hi)
+                want = seq.get_pcm_range(lo, hi)
+                assert pcm.dtype == np.int16 and off.dtype == np.int64 and valid.dtype == np.int32
+                assert len(off) == len(valid) == len(want) and (off + valid <= len(pcm)).all() and (off >= 0).all()
+                got = np.zeros_like(want)
+                for r in range(len(want)):
+                    got[r, :valid[r]] = pcm[off[r]:off[r] + valid[r]]
+                np.testing.assert_array_equal(got, want)
+    seq = dataset.SegmentSequence(wavs, bsz=125)
+    pcm, off, valid = seq.get_track_block(0, 1)
+    assert len(pcm) < 0.6 * seq.n_samples * 8000            # overlapping segments: about half the samples of the cut rows
+    assert (valid[valid < 8000] == 5000).all() and (valid < 8000).sum() == 1      # the 5000-sample file
