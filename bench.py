@@ -348,8 +348,8 @@ def run_gpu(args):
         x_dev = torch.empty((FP_SEGS_PER_STEP, 8000), dtype=torch.float32, device=dev)
         check(lib.nafp_synth_audio(ctx.h, 5, rank * FP_SEGS_PER_STEP, FP_SEGS_PER_STEP, ctypes.c_void_p(x_dev.data_ptr())))
         emb_dev = torch.empty((FP_SEGS_PER_STEP, 128), dtype=torch.float32, device=dev)
-        # e2e goes the way generate.py does: int16 PCM segments from pinned host memory (the / 2**15 of
-        # audio_utils.py:243-244 runs on the GPU), fingerprints back to host memory
+        # e2e: int16 PCM segments from pinned host memory (the / 2**15 of audio_utils.py:243-244 runs on the GPU),
+        # fingerprints back to host memory
         # one e2e step = one call of generate.py's size (batches_per_call 64 x TS_BATCH_SZ 125 = two encoder passes: the
         # upload of the second runs under the kernels of the first)
         x_pin = (x_dev.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16).cpu().repeat(FP_E2E_SEGS // FP_SEGS_PER_STEP, 1).pin_memory()
@@ -373,7 +373,8 @@ def run_gpu(args):
               "segments_per_step": segs, "dtype": "fp16 operands, fp32 accumulate",
               "e2e": {"value": FP_E2E_SEGS * world / (ms_fp_e2e * 1e-3), "unit": "segments/s", "segments_per_step": FP_E2E_SEGS * world,
                       "h2d_bytes_per_step": FP_E2E_SEGS * 16000, "d2h_bytes_per_step": FP_E2E_SEGS * 512,
-                      "through": "nafp_fingerprint_pcm16_host (what model/generate.py calls)"},
+                      "through": "nafp_fingerprint_pcm16_host ((n, 8000) int16 rows from pinned host memory; model/generate.py's "
+                                 "track-window entry point uploads half as many samples)"},
               "gpu_launches_per_step": int(fp_launches),
               "roofline": {"kernel": "conv_gemm_kernel (encoder, whole step)", "bound": "tensor", "achieved": tfl,
                            "peak": tf_sustained, "unit": "TFLOP/s", "frac": tfl / tf_sustained, "traffic": None,
