@@ -195,7 +195,9 @@ class ShardedFlatIndex:
         import torch
         if self.rank == 0:
             self.index.train(x, seed=seed)
-        if self.world > 1 or self.comm is not None and self.comm.world > 1:
+        if self.world > 1 and self.comm is None:
+            raise ValueError("a row-sharded IVF index needs a communicator (comm=TorchComm()) to share its quantizers")
+        if self.world > 1:
             dev = torch.device('cuda', self.index.ctx.device) if torch.cuda.is_available() else torch.device('cpu')
             coarse = torch.empty((self.index.nlist, 128), dtype=torch.float32, device=dev)
             pq = torch.empty((self.index.pq_m, 256, 128 // self.index.pq_m), dtype=torch.float32, device=dev) if self._ivfpq else None
