@@ -100,6 +100,11 @@ int nafp_weights_load(nafp_ctx* ctx, const float* const* conv_w, const float* co
 int nafp_logmel_forward(nafp_ctx* ctx, const float* x_dev, int64_t n_seg, int64_t group_size,
                         float* mel_dev);
 
+/* MODEL.FEAT (config/default.yaml:38): enable != 0 selects 'melspec_maxnorm' = Melspec_layer(segment_norm=True)
+ * (melspectrogram.py:110-111: x = (x - min/2) / |min/2 + 1e-10| over the batch tensor, after the max subtraction and
+ * the clamp) for nafp_logmel_forward and the nafp_fingerprint* entry points of this ctx; 0 (default) = 'melspec'. */
+int nafp_logmel_set_segment_norm(nafp_ctx* ctx, int32_t enable);
+
 /* FingerPrinter encoder: mel_dev (n_seg,256,32) float32 -> emb_dev (n_seg,128) float32,
  * L2-normalised (model/fp/nnfp.py:224-231).  Requires nafp_weights_load. */
 int nafp_encoder_forward(nafp_ctx* ctx, const float* mel_dev, int64_t n_seg, float* emb_dev);
@@ -229,6 +234,25 @@ int nafp_seq_top_dev(nafp_ctx* ctx, int64_t n_test, int32_t n_len, const int64_t
 /* merge n_shards top-k lists: D_all/I_all (n_shards, nq, k) -> (nq, k), ordered by (distance, label) */
 int nafp_topk_merge_dev(nafp_ctx* ctx, const float* D_all_dev, const int64_t* I_all_dev,
                         int32_t n_shards, int64_t nq, int32_t k, float* D_out_dev, int64_t* I_out_dev);
+
+/* ------------------------------------------------------------------ in-training mini search
+ * Replaces the TensorFlow / numpy work of model/utils/mini_search_subroutines.py, called from
+ * mini_search_validation (model/trainer.py:80-108).
+ *   q_host   (n_q, n_aug, d) float32 query embeddings, db_host (n_db, d) float32 (d is 128 for g(f), 1024 for f). */
+/* pairwise_distances_for_eval (:29-90): out_host (n_aug, n_q, n_db) float32 -- dot products when return_dotprod != 0,
+ * else max(|a|^2 + |b|^2 - 2 a.b, 0), its square root (zeros kept) when squared == 0. */
+int nafp_pairwise_dists_host(nafp_ctx* ctx, const float* q_host, const float* db_host, int64_t n_q, int64_t n_aug,
+                             int64_t n_db, int64_t d, int32_t return_dotprod, int32_t squared, float* out_host);
+/* conv_eye_func (:93-120): x_host (n_aug, n_q, n_db) -> out_host (n_aug, n_q-s+1, n_db-s+1),
+ * out[a,i,j] = sum_{t<s} x[a,i+t,j+t] (Conv2D with an s x s identity kernel, 'valid'). */
+int nafp_conv_eye_host(nafp_ctx* ctx, const float* x_host, int64_t n_aug, int64_t n_q, int64_t n_db, int32_t s,
+                       float* out_host);
+/* mini_search_eval (:123-236): for every scope s, target i < n_q-s+1 and augmentation a the rank of item
+ * gt = i + gt_id_offset in argsort(conv[a,i,:]) (descending for argmax != 0, which works on dot products);
+ * outputs per scope: top-1/3/10 accuracy in percent and the mean rank (doubles, n_scopes each). */
+int nafp_mini_search_host(nafp_ctx* ctx, const float* q_host, const float* db_host, int64_t n_q, int64_t n_aug,
+                          int64_t n_db, int64_t d, const int32_t* scopes, int32_t n_scopes, int32_t argmax,
+                          int64_t gt_id_offset, double* top1, double* top3, double* top10, double* mean_rank);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ _SIGS = {
     "nafp_synth_audio": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "nafp_weights_load": (c_int, [c_void_p, POINTER(_fp), POINTER(_fp), POINTER(_fp), POINTER(_fp), _fp, _fp, _fp, _fp]),
     "nafp_logmel_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "nafp_logmel_set_segment_norm": (c_int, [c_void_p, c_int32]),
     "nafp_encoder_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "nafp_fingerprint": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "nafp_fingerprint_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
@@ -91,6 +92,10 @@ _SIGS = {
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "nafp_seq_top_dev": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nafp_topk_merge_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
+    "nafp_pairwise_dists_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p]),
+    "nafp_conv_eye_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "nafp_mini_search_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int32, c_int32,
+                                      c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _f = getattr(lib, _name)

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing unless a profiler injects itself
+
 #include "../../include/nafp.h"
 
 namespace nafp {
@@ -40,6 +42,16 @@ const char* get_error();
         int _s = (expr);           \
         if (_s != NAFP_OK) return _s; \
     } while (0)
+
+// NVTX range around every compute entry point of the C ABI (the tracing hook of this path;
+// `nsys` / `ncu --nvtx` show them, e.g. `ncu --nvtx --nvtx-include "nafp_fingerprint/"`)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NAFP_RANGE(name) nafp::NvtxRange _nvtx_range_(name)
 
 struct LogmelState;
 struct EncoderState;

@@ -1189,6 +1189,7 @@ int nafp_index_destroy(nafp_index* idx) {
 }
 
 int nafp_index_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
+    NAFP_RANGE("nafp_index_train");
     NAFP_REQUIRE(idx, NAFP_ERR_INVALID, "nafp_index_train: idx is NULL");
     if (idx->type == NAFP_INDEX_FLAT_L2) return NAFP_OK;
     NAFP_REQUIRE(x_host && n > 0, NAFP_ERR_INVALID, "nafp_index_train: empty training set");
@@ -1207,8 +1208,14 @@ static int add_common(nafp_index* idx, const float* x, int64_t n, bool host) {
     if (idx->type != NAFP_INDEX_FLAT_L2) NAFP_TRY(ivfpq_add_rows(idx, row0, n));
     return NAFP_OK;
 }
-int nafp_index_add(nafp_index* idx, const float* x_host, int64_t n) { return add_common(idx, x_host, n, true); }
-int nafp_index_add_dev(nafp_index* idx, const float* x_dev, int64_t n) { return add_common(idx, x_dev, n, false); }
+int nafp_index_add(nafp_index* idx, const float* x_host, int64_t n) {
+    NAFP_RANGE("nafp_index_add");
+    return add_common(idx, x_host, n, true);
+}
+int nafp_index_add_dev(nafp_index* idx, const float* x_dev, int64_t n) {
+    NAFP_RANGE("nafp_index_add_dev");
+    return add_common(idx, x_dev, n, false);
+}
 
 int nafp_index_reserve(nafp_index* idx, int64_t n_total) {
     NAFP_REQUIRE(idx && n_total >= 0, NAFP_ERR_INVALID, "nafp_index_reserve: bad arguments");
@@ -1235,6 +1242,7 @@ int nafp_index_set_label_offset(nafp_index* idx, int64_t offset) {
 }
 
 int nafp_index_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    NAFP_RANGE("nafp_index_search_dev");
     NAFP_REQUIRE(idx && nq >= 0 && (nq == 0 || (q_dev && D_dev && I_dev)), NAFP_ERR_INVALID,
                  "nafp_index_search_dev: bad arguments");
     if (idx->type != NAFP_INDEX_FLAT_L2) return ivfpq_search_dev(idx, q_dev, nq, k, D_dev, I_dev);
@@ -1242,6 +1250,7 @@ int nafp_index_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k
 }
 
 int nafp_index_search(nafp_index* idx, const float* q_host, int64_t nq, int k, float* D_host, int64_t* I_host) {
+    NAFP_RANGE("nafp_index_search");
     NAFP_REQUIRE(idx && nq >= 0 && (nq == 0 || (q_host && D_host && I_host)), NAFP_ERR_INVALID,
                  "nafp_index_search: bad arguments");
     NAFP_REQUIRE(k >= 1 && k <= MAX_K, NAFP_ERR_INVALID, "search: k=%d outside [1,%d]", k, MAX_K);
@@ -1277,6 +1286,7 @@ int nafp_index_search(nafp_index* idx, const float* q_host, int64_t nq, int k, f
 }
 
 int nafp_index_reconstruct_host(nafp_index* idx, int64_t i0, int64_t n, float* out_host) {
+    NAFP_RANGE("nafp_index_reconstruct_host");
     NAFP_REQUIRE(idx && out_host && i0 >= 0 && n >= 0 && i0 + n <= idx->n, NAFP_ERR_INVALID,
                  "nafp_index_reconstruct_host: range [%lld, %lld) outside [0, %lld)", (long long)i0,
                  (long long)(i0 + n), (long long)(idx ? idx->n : 0));

@@ -166,21 +166,35 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int ld, int dim,
     out[idx] = x[static_cast<int64_t>(rows[idx / dim]) * ld + idx % dim];
 }
 
+// Seeded choice of `cnt` of n rows, defined so that any implementation can reproduce it (the oracle does, in numpy:
+// oracle/ivfpq_index.py select_rows): row i gets the key splitmix64(seed * 0xD1342543DE82EF95 + i); the cnt rows with
+// the smallest (key, i) are chosen and returned in ascending row order.
+static inline uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static std::vector<int64_t> select_rows(int64_t n, int64_t cnt, uint64_t seed) {
+    std::vector<std::pair<uint64_t, int64_t>> keyed(static_cast<size_t>(n));
+    const uint64_t base = seed * 0xD1342543DE82EF95ull;
+    for (int64_t i = 0; i < n; ++i) keyed[i] = {splitmix64(base + static_cast<uint64_t>(i)), i};
+    if (cnt > n) cnt = n;
+    std::nth_element(keyed.begin(), keyed.begin() + cnt, keyed.end());
+    std::vector<int64_t> rows(static_cast<size_t>(cnt));
+    for (int64_t i = 0; i < cnt; ++i) rows[i] = keyed[i].second;
+    std::sort(rows.begin(), rows.end());
+    return rows;
+}
+
 static int run_kmeans(nafp_ctx* ctx, const float* x_dev, int64_t n, int ld, int dim, int k, float* cent_dev,
                       int32_t* assign_dev, int niter, uint64_t seed) {
-    // initial centroids: k distinct training points chosen by a seeded shuffle
-    std::vector<int32_t> rows(n);
-    std::iota(rows.begin(), rows.end(), 0);
-    std::mt19937_64 rng(seed);
-    for (int64_t i = 0; i < std::min<int64_t>(k, n); ++i) {
-        std::uniform_int_distribution<int64_t> pick(i, n - 1);
-        std::swap(rows[i], rows[pick(rng)]);
-    }
-    std::sort(rows.begin(), rows.begin() + std::min<int64_t>(k, n));
+    // initial centroids: k distinct training points (select_rows), in ascending row order
+    const std::vector<int64_t> rows = select_rows(n, k, seed);
     int32_t* rows_dev = nullptr;
     NAFP_CUDA(cudaMalloc(&rows_dev, k * sizeof(int32_t)));
     std::vector<int32_t> first(k);
-    for (int i = 0; i < k; ++i) first[i] = rows[i % std::max<int64_t>(n, 1)];
+    for (int i = 0; i < k; ++i) first[i] = static_cast<int32_t>(rows[i % std::max<size_t>(rows.size(), 1)]);
     NAFP_CUDA(cudaMemcpyAsync(rows_dev, first.data(), k * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     gather_rows_kernel<<<(k * dim + 255) / 256, 256, 0, ctx->stream>>>(x_dev, ld, dim, rows_dev, k, cent_dev);
     const int threads = 256, warps = threads / 32;
@@ -422,8 +436,12 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
                 buf[slot] = key;         // slot < CAP: the buffer is pruned whenever fewer than 256 slots remain
             }
         }
+        // block-uniform decision: every thread reads the counter between two barriers, so that a warp that is
+        // already inserting the next iteration's keys cannot make a slower warp take the branch alone
         __syncthreads();
-        if (cnt_s > IVF_SCAN_CAP - 256) {
+        const int filled = cnt_s;
+        __syncthreads();
+        if (filled > IVF_SCAN_CAP - 256) {
             block_sort_asc_u64(buf, IVF_SCAN_CAP);
             for (int e = k + tid; e < IVF_SCAN_CAP; e += blockDim.x) buf[e] = ~0ull;
             if (tid == 0) { cnt_s = k; thr_s = buf[k - 1]; }
@@ -485,7 +503,9 @@ ivfflat_scan_kernel(const float* __restrict__ q, int64_t nq, const int32_t* __re
             }
         }
         __syncthreads();
-        if (cnt_s > IVF_SCAN_CAP - 8 * ROWS_PER_WARP) {
+        const int filled = cnt_s;           // block-uniform (see ivfpq_scan_kernel)
+        __syncthreads();
+        if (filled > IVF_SCAN_CAP - 8 * ROWS_PER_WARP) {
             block_sort_asc_u64(buf, IVF_SCAN_CAP);
             for (int e = k + tid; e < IVF_SCAN_CAP; e += blockDim.x) buf[e] = ~0ull;
             if (tid == 0) { cnt_s = k; thr_s = buf[k - 1]; }
@@ -601,11 +621,11 @@ int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits) {
     s->nlist = nlist;
     s->m = m;
     s->dsub = D128 / m;
+    idx->ivf = s;                  // before the first fallible call: nafp_index_destroy releases it
     NAFP_CUDA(cudaMalloc(&s->coarse, static_cast<size_t>(nlist) * D128 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->pq, static_cast<size_t>(m) * PQ_KSUB * s->dsub * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->loff, (nlist + 1) * sizeof(int32_t)));
     NAFP_CUDA(cudaMalloc(&s->xhat_tmp, static_cast<size_t>(RECON_CHUNK) * D128 * sizeof(float)));
-    idx->ivf = s;
     NAFP_TRY(nafp_index_create(idx->ctx, NAFP_INDEX_FLAT_L2, D128, 0, 0, 8, &s->recon));
     return NAFP_OK;
 }
@@ -627,22 +647,17 @@ int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
     NAFP_CUDA(cudaSetDevice(ctx->device));
     // faiss-style subsampling: at most 256 training points per centroid
     const int64_t max_pts = 256ll * (s->flat_lists ? s->nlist : std::max(s->nlist, PQ_KSUB));
-    std::vector<int64_t> rows(n);
-    std::iota(rows.begin(), rows.end(), 0);
-    int64_t nt = n;
-    if (n > max_pts) {
-        std::mt19937_64 rng(static_cast<uint64_t>(seed));
-        for (int64_t i = 0; i < max_pts; ++i) {
-            std::uniform_int_distribution<int64_t> pick(i, n - 1);
-            std::swap(rows[i], rows[pick(rng)]);
-        }
-        nt = max_pts;
-        std::sort(rows.begin(), rows.begin() + nt);
-    }
+    const std::vector<int64_t> rows = select_rows(n, n > max_pts ? max_pts : n, static_cast<uint64_t>(seed));
+    const int64_t nt = static_cast<int64_t>(rows.size());
     std::vector<float> xt(static_cast<size_t>(nt) * D128);
     for (int64_t i = 0; i < nt; ++i) memcpy(&xt[i * D128], x_host + rows[i] * D128, D128 * sizeof(float));
     float *x_dev = nullptr, *r_dev = nullptr;
     int32_t* a_dev = nullptr;
+    struct Guard {                 // the temporaries (several hundred MB) are released on every return path
+        float **x, **r;
+        int32_t** a;
+        ~Guard() { cudaFree(*x); cudaFree(*r); cudaFree(*a); }
+    } guard{&x_dev, &r_dev, &a_dev};
     NAFP_CUDA(cudaMalloc(&x_dev, xt.size() * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&r_dev, xt.size() * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&a_dev, nt * sizeof(int32_t)));
@@ -650,9 +665,6 @@ int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
     NAFP_TRY(run_kmeans(ctx, x_dev, nt, D128, D128, s->nlist, s->coarse, a_dev, 25, static_cast<uint64_t>(seed) + 1));
     if (s->flat_lists) {
         NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(x_dev);
-        cudaFree(r_dev);
-        cudaFree(a_dev);
         s->trained = true;
         return NAFP_OK;
     }
@@ -666,9 +678,6 @@ int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
                             s->pq + static_cast<size_t>(sub) * PQ_KSUB * s->dsub, a_dev, 25,
                             static_cast<uint64_t>(seed) + 2 + sub));
     NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(x_dev);
-    cudaFree(r_dev);
-    cudaFree(a_dev);
     s->trained = true;
     return NAFP_OK;
 }
@@ -738,6 +747,11 @@ static int build_lists(nafp_index* idx) {
     if (nchunks > 0) {
         int32_t* hist = nullptr;
         int64_t* base = nullptr;
+        struct Guard {             // released on every return path
+            int32_t** h;
+            int64_t** b;
+            ~Guard() { cudaFree(*h); cudaFree(*b); }
+        } guard{&hist, &base};
         NAFP_CUDA(cudaMalloc(&hist, static_cast<size_t>(s->nlist) * nchunks * sizeof(int32_t)));
         NAFP_CUDA(cudaMalloc(&base, static_cast<size_t>(s->nlist) * nchunks * sizeof(int64_t)));
         ivf_hist_kernel<<<nchunks, 32, 0, ctx->stream>>>(s->assign, n, s->nlist, hist);
@@ -759,8 +773,6 @@ static int build_lists(nafp_index* idx) {
         ctx->launches += 2;
         NAFP_CUDA(cudaGetLastError());
         NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(hist);
-        cudaFree(base);
     }
     NAFP_CUDA(cudaMemcpy(s->loff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     s->dirty = false;
@@ -905,6 +917,7 @@ int nafp_index_is_trained(nafp_index* idx) {
 }
 
 int nafp_index_ivf_get_coarse(nafp_index* idx, float* coarse_host) {
+    NAFP_RANGE("nafp_index_ivf_get_coarse");
     NAFP_REQUIRE(idx && idx->ivf && coarse_host, NAFP_ERR_INVALID, "nafp_index_ivf_get_coarse: not an IVF index");
     IvfPq* s = idx->ivf;
     NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "nafp_index_ivf_get_coarse: index is not trained");
@@ -914,6 +927,7 @@ int nafp_index_ivf_get_coarse(nafp_index* idx, float* coarse_host) {
 }
 
 int nafp_index_ivf_set_coarse(nafp_index* idx, const float* coarse_host) {
+    NAFP_RANGE("nafp_index_ivf_set_coarse");
     NAFP_REQUIRE(idx && idx->ivf && coarse_host, NAFP_ERR_INVALID, "nafp_index_ivf_set_coarse: not an IVF index");
     NAFP_REQUIRE(idx->n == 0, NAFP_ERR_STATE, "nafp_index_ivf_set_coarse: index already holds rows");
     IvfPq* s = idx->ivf;
@@ -923,6 +937,7 @@ int nafp_index_ivf_set_coarse(nafp_index* idx, const float* coarse_host) {
 }
 
 int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_host) {
+    NAFP_RANGE("nafp_index_ivfpq_get_params");
     NAFP_REQUIRE(idx && idx->ivf && !idx->ivf->flat_lists && coarse_host && pq_host, NAFP_ERR_INVALID,
                  "nafp_index_ivfpq_get_params: not an IVF-PQ index");
     IvfPq* s = idx->ivf;
@@ -934,6 +949,7 @@ int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_h
 }
 
 int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const float* pq_host) {
+    NAFP_RANGE("nafp_index_ivfpq_set_params");
     NAFP_REQUIRE(idx && idx->ivf && !idx->ivf->flat_lists && coarse_host && pq_host, NAFP_ERR_INVALID,
                  "nafp_index_ivfpq_set_params: not an IVF-PQ index");
     NAFP_REQUIRE(idx->n == 0, NAFP_ERR_STATE, "nafp_index_ivfpq_set_params: index already holds rows");

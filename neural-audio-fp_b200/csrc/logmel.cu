@@ -35,8 +35,9 @@ static_assert(2 * 64 * 9 >= 512, "Q must hold mag");
 struct LogmelState {
     float* melw = nullptr;     // [MAXTAPS][NMEL]
     int* start = nullptr;      // [NMEL]
-    int32_t* gmax = nullptr;   // [groups] ordered-int group maxima
+    int32_t* gmax = nullptr;   // [2][cap] ordered-int group maxima, then group minima
     int64_t gmax_cap = 0;
+    bool segment_norm = false; // MODEL.FEAT == 'melspec_maxnorm' (melspectrogram.py:110-111)
 };
 
 // ---- 8-point FFT, natural order in and out
@@ -86,12 +87,12 @@ template <typename TIn>
 __global__ void __launch_bounds__(256, 2)
 logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, const float* __restrict__ melw,
               const int* __restrict__ start, float* __restrict__ out, int32_t* __restrict__ gmax,
-              const int64_t* __restrict__ seg_off, const int32_t* __restrict__ seg_valid) {
+              int32_t* __restrict__ gmin, const int64_t* __restrict__ seg_off, const int32_t* __restrict__ seg_valid) {
     extern __shared__ float smem[];
     float* xs = smem;                                  // [PADDED]
     float* grp = xs + PADDED;                          // 4 x GRP_FLOATS
     float* tile = grp + 4 * GRP_FLOATS;                // [NMEL][TILE_LD]
-    __shared__ float wmax[8];
+    __shared__ float wmax[8], wmin[8];
 
     const int64_t seg = blockIdx.x;
     const int tid = threadIdx.x;
@@ -135,7 +136,7 @@ logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, cons
     float* Zim = P + 512;
     float* mag = Q;
     const int bar_id = 1 + g;
-    float lmax = -INFINITY;
+    float lmax = -INFINITY, lmin = INFINITY;
     __syncthreads();
 
     for (int it = 0; it < NFRAMES / 4; ++it) {
@@ -208,18 +209,23 @@ logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, cons
             const float y = log10f(fmaxf(acc + 0.06f, 1e-10f));
             tile[f * TILE_LD + frame] = y;
             lmax = fmaxf(lmax, y);
+            lmin = fminf(lmin, y);
         }
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // mag reads done before next frame's S2 writes
     }
 
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-    if ((tid & 31) == 0) wmax[tid >> 5] = lmax;
+    for (int o = 16; o > 0; o >>= 1) {
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    }
+    if ((tid & 31) == 0) { wmax[tid >> 5] = lmax; wmin[tid >> 5] = lmin; }
     __syncthreads();
     if (tid == 0) {
-        float m = wmax[0];
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, wmax[w]);
+        float m = wmax[0], mn = wmin[0];
+        for (int w = 1; w < 8; ++w) { m = fmaxf(m, wmax[w]); mn = fminf(mn, wmin[w]); }
         atomicMax(gmax + seg / group_size, f2ord(m));
+        if (gmin) atomicMin(gmin + seg / group_size, f2ord(mn));      // only the segment_norm branch reads it
     }
     float* o = out + seg * (NMEL * NFRAMES);
     for (int i = tid; i < NMEL * NFRAMES / 4; i += 256) {
@@ -234,18 +240,28 @@ __global__ void logmel_fill_kernel(int32_t* p, int64_t n, int32_t v) {
     if (i < n) p[i] = v;
 }
 
-// y = max(y - group_max, -80)   (melspectrogram.py:108-109)
+// y = max(y - group_max, -80)   (melspectrogram.py:108-109); with gmin != NULL also the 'melspec_maxnorm' branch
+// y = (y - min / 2) / |min / 2 + 1e-10| (:110-111), min = the group's minimum AFTER the subtraction and the clamp
 __global__ void logmel_finish_kernel(float* __restrict__ out, int64_t n_seg, int64_t group_size,
-                                     const int32_t* __restrict__ gmax) {
+                                     const int32_t* __restrict__ gmax, const int32_t* __restrict__ gmin) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // float4 index
     const int64_t per_seg = NMEL * NFRAMES / 4;
     if (i >= n_seg * per_seg) return;
-    const float m = ord2f(gmax[(i / per_seg) / group_size]);
+    const int64_t grp = (i / per_seg) / group_size;
+    const float m = ord2f(gmax[grp]);
     float4 v = reinterpret_cast<float4*>(out)[i];
     v.x = fmaxf(v.x - m, -80.f);
     v.y = fmaxf(v.y - m, -80.f);
     v.z = fmaxf(v.z - m, -80.f);
     v.w = fmaxf(v.w - m, -80.f);
+    if (gmin) {
+        const float half = fmaxf(ord2f(gmin[grp]) - m, -80.f) / 2.f;
+        const float den = fabsf(half + 1e-10f);
+        v.x = (v.x - half) / den;
+        v.y = (v.y - half) / den;
+        v.z = (v.z - half) / den;
+        v.w = (v.w - half) / den;
+    }
     reinterpret_cast<float4*>(out)[i] = v;
 }
 
@@ -322,22 +338,29 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
         if (s->gmax) NAFP_CUDA(cudaFree(s->gmax));
         s->gmax = nullptr;
         s->gmax_cap = 0;
-        NAFP_CUDA(cudaMalloc(&s->gmax, static_cast<size_t>(groups) * sizeof(int32_t)));
+        NAFP_CUDA(cudaMalloc(&s->gmax, 2 * static_cast<size_t>(groups) * sizeof(int32_t)));
         s->gmax_cap = groups;
     }
+    int32_t* gmin = s->segment_norm ? s->gmax + s->gmax_cap : nullptr;
+    NAFP_REQUIRE(finish || !s->segment_norm, NAFP_ERR_STATE, "logmel: melspec_maxnorm needs the finishing pass");
     logmel_fill_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, ctx->stream>>>(
-        s->gmax, groups, static_cast<int32_t>(0x807FFFFFu));
+        s->gmax, groups, static_cast<int32_t>(0x807FFFFFu));                 // f2ord(-inf)
+    if (gmin) {
+        logmel_fill_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, ctx->stream>>>(
+            gmin, groups, static_cast<int32_t>(0x7F800000u));                // f2ord(+inf)
+        ctx->launches++;
+    }
     if (pcm16)
         logmel_kernel<int16_t><<<static_cast<unsigned>(n_seg), 256, LOGMEL_SMEM, ctx->stream>>>(
-            static_cast<const int16_t*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, seg_off, seg_valid);
+            static_cast<const int16_t*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, gmin, seg_off, seg_valid);
     else
         logmel_kernel<float><<<static_cast<unsigned>(n_seg), 256, LOGMEL_SMEM, ctx->stream>>>(
-            static_cast<const float*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, seg_off, seg_valid);
+            static_cast<const float*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, gmin, seg_off, seg_valid);
     ctx->launches += 2;
     if (finish) {
         const int64_t n4 = n_seg * (NMEL * NFRAMES / 4);
         logmel_finish_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, ctx->stream>>>(mel_dev, n_seg, group_size,
-                                                                                             s->gmax);
+                                                                                             s->gmax, gmin);
         ctx->launches++;
     }
     NAFP_CUDA(cudaGetLastError());
@@ -345,10 +368,23 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
     return NAFP_OK;
 }
 
+bool logmel_segment_norm(nafp_ctx* ctx) { return ctx->logmel && ctx->logmel->segment_norm; }
+
 }  // namespace nafp
+
+/* MODEL.FEAT: 0 = 'melspec' (default), 1 = 'melspec_maxnorm' (Melspec_layer(segment_norm=True), melspectrogram.py:110-111) */
+extern "C" int nafp_logmel_set_segment_norm(nafp_ctx* ctx, int32_t enable) {
+    NAFP_REQUIRE(ctx, NAFP_ERR_INVALID, "nafp_logmel_set_segment_norm: ctx is NULL");
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    NAFP_TRY(nafp::logmel_init(ctx));
+    NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->logmel->segment_norm = enable != 0;
+    return NAFP_OK;
+}
 
 extern "C" int nafp_logmel_forward(nafp_ctx* ctx, const float* x_dev, int64_t n_seg, int64_t group_size,
                                    float* mel_dev) {
+    NAFP_RANGE("nafp_logmel_forward");
     NAFP_REQUIRE(ctx, NAFP_ERR_INVALID, "nafp_logmel_forward: ctx is NULL");
     return nafp::logmel_run(ctx, x_dev, false, n_seg, group_size, mel_dev, true, nullptr, nullptr, nullptr);
 }

@@ -320,6 +320,7 @@ extern "C" {
 int nafp_seq_plan_dev(nafp_ctx* ctx, const int64_t* test_ids_dev, int64_t n_test, int32_t max_len,
                       int64_t n_query_rows, int32_t* scratch_dev, int32_t* rowmap_dev, int32_t* uniq_rows_dev,
                       int64_t* n_uniq_out) {
+    NAFP_RANGE("nafp_seq_plan_dev");
     NAFP_REQUIRE(ctx && test_ids_dev && scratch_dev && rowmap_dev && uniq_rows_dev && n_uniq_out && n_test >= 0 &&
                      max_len >= 1 && max_len <= SEQ_MAXL && n_query_rows >= 0 && n_query_rows < (1ll << 31),
                  NAFP_ERR_INVALID, "nafp_seq_plan_dev: bad arguments (max_len <= %d)", SEQ_MAXL);
@@ -346,6 +347,7 @@ int nafp_seq_plan_dev(nafp_ctx* ctx, const int64_t* test_ids_dev, int64_t n_test
 
 int nafp_seq_gather_rows_dev(nafp_ctx* ctx, const float* q_dev, const int32_t* rows_dev, int64_t n_rows,
                              float* out_dev) {
+    NAFP_RANGE("nafp_seq_gather_rows_dev");
     NAFP_REQUIRE(ctx && n_rows >= 0 && (n_rows == 0 || (q_dev && rows_dev && out_dev)), NAFP_ERR_INVALID,
                  "nafp_seq_gather_rows_dev: bad arguments");
     if (n_rows == 0) return NAFP_OK;
@@ -360,6 +362,7 @@ int nafp_seq_cand_dev(nafp_index* idx, const float* q_dev, int64_t n_query_rows,
                       int64_t n_test, const int32_t* seq_lens_dev, int32_t n_len, int32_t max_len, int32_t k_probe,
                       const int64_t* I_dev, const int32_t* rowmap_dev, int64_t n_rows_global, int64_t owned_lo,
                       int64_t owned_hi, int64_t* cand_ids_dev, float* cand_scores_dev, int32_t* n_cand_dev) {
+    NAFP_RANGE("nafp_seq_cand_dev");
     NAFP_REQUIRE(idx && q_dev && test_ids_dev && seq_lens_dev && I_dev && cand_ids_dev && cand_scores_dev &&
                      n_cand_dev, NAFP_ERR_INVALID, "nafp_seq_cand_dev: NULL argument");
     NAFP_REQUIRE(max_len >= 1 && max_len <= SEQ_MAXL && k_probe >= 1 && max_len * k_probe <= SEQ_MAXC &&
@@ -379,6 +382,7 @@ int nafp_seq_cand_dev(nafp_index* idx, const float* q_dev, int64_t n_query_rows,
 int nafp_seq_top_dev(nafp_ctx* ctx, int64_t n_test, int32_t n_len, const int64_t* cand_ids_dev,
                      const float* cand_scores_dev, const int32_t* n_cand_dev, int64_t* pred_ids_dev,
                      float* pred_scores_dev) {
+    NAFP_RANGE("nafp_seq_top_dev");
     NAFP_REQUIRE(ctx && cand_ids_dev && cand_scores_dev && n_cand_dev && pred_ids_dev && n_len >= 1,
                  NAFP_ERR_INVALID, "nafp_seq_top_dev: bad arguments");
     if (n_test == 0) return NAFP_OK;
@@ -391,6 +395,7 @@ int nafp_seq_top_dev(nafp_ctx* ctx, int64_t n_test, int32_t n_len, const int64_t
 
 int nafp_topk_merge_dev(nafp_ctx* ctx, const float* D_all_dev, const int64_t* I_all_dev, int32_t n_shards,
                         int64_t nq, int32_t k, float* D_out_dev, int64_t* I_out_dev) {
+    NAFP_RANGE("nafp_topk_merge_dev");
     NAFP_REQUIRE(ctx && D_all_dev && I_all_dev && D_out_dev && I_out_dev && n_shards >= 1 && k >= 1 &&
                      n_shards * k <= 2048, NAFP_ERR_INVALID, "nafp_topk_merge_dev: need n_shards*k <= 2048");
     if (nq == 0) return NAFP_OK;
@@ -404,6 +409,7 @@ int nafp_topk_merge_dev(nafp_ctx* ctx, const float* D_all_dev, const int64_t* I_
 int nafp_seq_match(nafp_index* idx, const float* q_host, int64_t n_query_rows, const int64_t* test_ids,
                    int64_t n_test, const int32_t* seq_lens, int32_t n_len, int32_t k_probe, int64_t* pred_ids_host,
                    float* pred_scores_host) {
+    NAFP_RANGE("nafp_seq_match");
     NAFP_REQUIRE(idx && q_host && test_ids && seq_lens && pred_ids_host && n_test >= 0 && n_len >= 1 &&
                      n_query_rows >= 0, NAFP_ERR_INVALID, "nafp_seq_match: bad arguments");
     if (n_test == 0) return NAFP_OK;

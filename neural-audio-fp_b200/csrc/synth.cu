@@ -86,6 +86,7 @@ extern "C" {
 
 int nafp_synth_fp_rows(nafp_ctx* ctx, int64_t seed, int64_t row0, int64_t n_rows, int32_t track_len, float rho,
                        float* out_dev) {
+    NAFP_RANGE("nafp_synth_fp_rows");
     NAFP_REQUIRE(ctx && out_dev && n_rows >= 0 && row0 >= 0 && track_len >= 1 && track_len <= 64, NAFP_ERR_INVALID,
                  "nafp_synth_fp_rows: bad arguments (track_len <= 64)");
     if (n_rows == 0) return NAFP_OK;
@@ -99,6 +100,7 @@ int nafp_synth_fp_rows(nafp_ctx* ctx, int64_t seed, int64_t row0, int64_t n_rows
 }
 
 int nafp_synth_audio(nafp_ctx* ctx, int64_t seed, int64_t seg0, int64_t n_seg, float* out_dev) {
+    NAFP_RANGE("nafp_synth_audio");
     NAFP_REQUIRE(ctx && out_dev && n_seg >= 0 && seg0 >= 0, NAFP_ERR_INVALID, "nafp_synth_audio: bad arguments");
     if (n_seg == 0) return NAFP_OK;
     NAFP_CUDA(cudaSetDevice(ctx->device));

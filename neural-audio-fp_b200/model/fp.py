@@ -23,8 +23,8 @@ def _check_model_cfg(cfg):
             raise NotImplementedError(f"MODEL.{k}={m[k]}: the B200 kernels are built for {v} (all reference configs)")
     if float(m['DUR']) != 1.0 or float(m['F_MIN']) != 300.0 or float(m['F_MAX']) != 4000.0:
         raise NotImplementedError("MODEL.DUR/F_MIN/F_MAX other than 1 s / 300 Hz / 4000 Hz are not built")
-    if m['FEAT'] != 'melspec':
-        raise NotImplementedError(f"MODEL.FEAT={m['FEAT']!r}: only 'melspec' is on the hot path")
+    if m['FEAT'] not in ('melspec', 'melspec_maxnorm'):      # model/generate.py:17-20 raises for anything else, too
+        raise NotImplementedError(m['FEAT'])
     if m['BN'] != 'layer_norm2d':
         raise NotImplementedError(f"MODEL.BN={m['BN']!r}: only 'layer_norm2d' is on the hot path")
 
@@ -33,8 +33,9 @@ class Melspec:
     """``m_pre``: (B,1,8000) float32 -> (B,256,32,1) float32; rows are grouped in consecutive
     ``group_size`` batches that share the batch-global max (``melspectrogram.py:108``)."""
 
-    def __init__(self, ctx=None, device=0):
+    def __init__(self, ctx=None, device=0, segment_norm=False):
         self.ctx = ctx or Context.get(device)
+        self.segment_norm = bool(segment_norm)       # MODEL.FEAT == 'melspec_maxnorm' (melspectrogram.py:110-111)
 
     def __call__(self, x, group_size=None):
         x = np.ascontiguousarray(x, dtype=np.float32)
@@ -50,6 +51,7 @@ class Melspec:
         od = self.ctx.malloc(out.nbytes)
         try:
             self.ctx.h2d(xd, x)
+            check(lib.nafp_logmel_set_segment_norm(self.ctx.h, int(self.segment_norm)))
             check(lib.nafp_logmel_forward(self.ctx.h, xd, n, g, od))
             self.ctx.d2h(out, od)
             self.ctx.sync()
@@ -62,9 +64,10 @@ class Melspec:
 class FingerPrinter:
     """``m_fp`` (+ the fused ``test_step``).  Weights live on the device after ``load``."""
 
-    def __init__(self, ctx=None, device=0):
+    def __init__(self, ctx=None, device=0, segment_norm=False):
         self.ctx = ctx or Context.get(device)
         self.loaded = False
+        self.segment_norm = bool(segment_norm)       # feature variant of the fused test_step entry points
 
     def load(self, weights):
         specs = arch.conv_specs()
@@ -126,6 +129,7 @@ class FingerPrinter:
             fn = lib.nafp_fingerprint_host
         if x.shape[1] != 8000:
             raise ValueError("expected 8000-sample segments")
+        check(lib.nafp_logmel_set_segment_norm(self.ctx.h, int(self.segment_norm)))
         check(fn(self.ctx.h, ptr(x), n, int(group_size), ptr(emb)))
         return emb
 
@@ -141,6 +145,7 @@ class FingerPrinter:
         emb = np.empty((n, 128), dtype=np.float32)
         if n == 0:
             return emb
+        check(lib.nafp_logmel_set_segment_norm(self.ctx.h, int(self.segment_norm)))
         check(lib.nafp_fingerprint_pcm16_tracks_host(self.ctx.h, ptr(pcm), len(pcm), ptr(seg_off), ptr(seg_valid), n,
                                                      int(group_size), ptr(emb)))
         return emb
@@ -157,7 +162,8 @@ def build_fp(cfg, device=0):
     """(m_pre, m_fp) -- ``model/generate.py:16-23``."""
     _check_model_cfg(cfg)
     ctx = Context.get(device)
-    return Melspec(ctx), FingerPrinter(ctx)
+    seg_norm = cfg['MODEL']['FEAT'] == 'melspec_maxnorm'
+    return Melspec(ctx, segment_norm=seg_norm), FingerPrinter(ctx, segment_norm=seg_norm)
 
 
 def test_step(X, m_pre, m_fp, group_size=None):

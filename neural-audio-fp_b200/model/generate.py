@@ -5,10 +5,15 @@ output_root_dir, skip_dummy)``), same outputs (``{key}.mm`` raw float32 C-order 
 ``{key}_shape.npy`` for key in dummy_db / query / db or custom_source, ``generate.py:122-161``), same
 batch grouping (consecutive ``BSZ.TS_BATCH_SZ`` segments share the log-mel max, ``:176-181``).
 
-Checkpoints: TensorFlow checkpoints cannot be read offline; weights come from the ``.npz`` exchange
-format of ``model/weights.py`` at ``{LOG_ROOT_DIR}checkpoint/{checkpoint_name}/ckpt-{index}.npz``.  The
-name ``random-init[:SEED]`` selects seeded Keras-default initialisation (what the reference would
-hold before training).
+Checkpoints: ``{LOG_ROOT_DIR}checkpoint/{checkpoint_name}/ckpt-{index}`` is either the ``.npz`` exchange format
+of ``model/weights.py`` or the reference's own TensorFlow checkpoint (``.index`` + ``.data-*``), which
+``model/tf_checkpoint.py`` reads without TensorFlow.  The name ``random-init[:SEED]`` selects seeded Keras-default
+initialisation (what the reference would hold before training).
+
+Multi-GPU (SURVEY §8 e, "split by segment batch with no collective"): started once per GPU -- ``torchrun`` or any
+launcher that sets RANK / WORLD_SIZE / LOCAL_RANK -- every rank fingerprints a contiguous range of whole
+TS_BATCH_SZ batches and writes its own rows of the shared memmap.  The only synchronisation is a barrier around the
+creation of each output file; it runs over a CPU (gloo) process group because no tensor ever crosses ranks.
 """
 from __future__ import annotations
 
@@ -93,11 +98,41 @@ def _shard(n_batches, rank, world):
     return lo, lo + per + (1 if rank < rem else 0)
 
 
+def distributed_env():
+    """(rank, world_size, device) of this process from the launcher's environment.  NAFP_DEVICE overrides the GPU
+    (default LOCAL_RANK): several ranks may share one GPU, e.g. in the 2-rank test on a single-GPU box."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    device = int(os.environ.get('NAFP_DEVICE', os.environ.get('LOCAL_RANK', '0')))
+    return rank, world, device
+
+
+def _barrier_fn(world_size):
+    """Barrier over the ranks of a generation job: a gloo (CPU) group -- the data path has no collective."""
+    if world_size <= 1:
+        return lambda: None
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('gloo')
+    group = dist.new_group(backend='gloo') if dist.get_backend() != 'gloo' else None
+    return lambda: dist.barrier(group=group)
+
+
 def generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source_root_dir, output_root_dir, skip_dummy,
-                         rank=0, world_size=1, device=None, batches_per_call=64):
-    """See the module docstring.  ``rank`` / ``world_size``: every rank fingerprints a contiguous range
-    of whole TS_BATCH_SZ batches on its own GPU and writes its rows of the shared memmap."""
-    m_pre, m_fp = build_fp(cfg, device=rank if device is None else device)
+                         rank=None, world_size=None, device=None, batches_per_call=64):
+    """See the module docstring.  ``rank`` / ``world_size`` / ``device`` default to the launcher's environment
+    (RANK, WORLD_SIZE, LOCAL_RANK): every rank fingerprints a contiguous range of whole TS_BATCH_SZ batches on its
+    own GPU and writes its rows of the shared memmap."""
+    env_rank, env_world, env_device = distributed_env()
+    rank = env_rank if rank is None else int(rank)
+    world_size = env_world if world_size is None else int(world_size)
+    if device is None:
+        device = env_device if world_size > 1 else 0
+    if not 0 <= rank < world_size:
+        raise ValueError(f'rank {rank} outside world_size {world_size}')
+    barrier = _barrier_fn(world_size)
+    m_pre, m_fp = build_fp(cfg, device=device)
     checkpoint_root_dir = cfg['DIR']['LOG_ROOT_DIR'] + 'checkpoint/'
     checkpoint_index = load_checkpoint(checkpoint_root_dir, checkpoint_name, checkpoint_index, m_fp)
 
@@ -122,11 +157,9 @@ def generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source_root_dir
         if rank == 0:
             arr = np.memmap(path, dtype='float32', mode='w+', shape=arr_shape)
             np.save(f'{output_root_dir}/{key}_shape.npy', arr_shape)
-        if world_size > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            if rank != 0:
-                arr = np.memmap(path, dtype='float32', mode='r+', shape=arr_shape)
+        barrier()                      # the file exists at its full size before any other rank maps it
+        if rank != 0:
+            arr = np.memmap(path, dtype='float32', mode='r+', shape=arr_shape)
 
         print(f"=== Generating fingerprint from \x1b[1;32m'{key}'\x1b[0m bsz={bsz}, {n_items} items, d={dim} ===")
         b_lo, b_hi = _shard(len(ds[key]), rank, world_size)
@@ -150,9 +183,7 @@ def generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source_root_dir
         sz_check[key] = len(arr)
         arr.flush()
         del arr
-        if world_size > 1:
-            import torch.distributed as dist
-            dist.barrier()
+        barrier()                      # every rank's rows are on disk before anyone moves on / returns
 
     if 'custom_source' in ds.keys():
         pass

@@ -41,10 +41,16 @@ def cli():
               help="Root directory where the generated embeddings (uncompressed) will be stored.")
 @click.option('--skip_dummy', default=False, is_flag=True, help='Exclude dummy-DB from the default source.')
 def generate(checkpoint_name, checkpoint_index, config, source, output, skip_dummy):
-    """Generate fingerprints from a saved checkpoint ('random-init[:SEED]' for seeded random weights)."""
-    from .model.generate import generate_fingerprint
+    """Generate fingerprints from a saved checkpoint ('random-init[:SEED]' for seeded random weights).
+
+    Under torchrun (one process per GPU: RANK / WORLD_SIZE / LOCAL_RANK) the batches are split over the ranks."""
+    from .model.generate import distributed_env, generate_fingerprint
     cfg = load_config(config)
-    generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source, output, skip_dummy)
+    rank, world, device = distributed_env()
+    if world > 1:
+        print(f'cli: rank {rank} of {world} on GPU {device}')
+    generate_fingerprint(cfg, checkpoint_name, checkpoint_index, source, output, skip_dummy,
+                         rank=rank, world_size=world, device=device)
 
 
 @cli.command()

@@ -76,3 +76,45 @@ def test_generate_then_evaluate(corpus):
     assert np.abs(np.array(rates) - seq_match.hit_rates(raw_o, 4)).max() <= 100.0 / len(test_ids) + 1e-9
     assert not os.path.exists(emb_dir + "dummy_db.mm.bak")
     assert os.path.getsize(emb_dir + "dummy_db.mm") == 12 * 23 * 128 * 4      # inputs are never extended on disk
+
+
+def _run_generate_ranks(cfg_path, out_dir, world, tmp):
+    """`run.py generate` once per rank, all ranks on GPU 0 (NAFP_DEVICE), the way torchrun would start them."""
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), NAFP_DEVICE="0",
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PYTHONPATH=ROOT)
+        log = open(os.path.join(tmp, f"gen_w{world}_r{rank}.log"), "w")
+        procs.append((subprocess.Popen([sys.executable, "-m", "nafp_b200.run", "generate", "random-init:7", "-c", cfg_path,
+                                        "-o", out_dir], env=env, cwd=ROOT, stdout=log, stderr=subprocess.STDOUT), log))
+    for p, log in procs:
+        rc = p.wait(timeout=600)
+        log.close()
+        assert rc == 0, open(log.name).read()[-2000:]
+
+
+def test_generate_sharded_over_two_ranks_is_byte_identical(corpus, tmp_path):
+    """SURVEY §8 e / north_star: generation is split by segment batch with no collective.  Two ranks (started like
+    torchrun starts them, gloo barrier around the file creation, both on this box's GPU) must write exactly the
+    bytes one rank writes -- batches are whole TS_BATCH_SZ groups, so every group's log-mel max is unchanged."""
+    cfg, _ = corpus
+    cfg_path = str(tmp_path / "cfg.yaml")
+    with open(cfg_path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    one, two = str(tmp_path / "w1"), str(tmp_path / "w2")
+    _run_generate_ranks(cfg_path, one, 1, str(tmp_path))
+    _run_generate_ranks(cfg_path, two, 2, str(tmp_path))
+    for key, rows in (("dummy_db", 12 * 23), ("query", 4 * 19), ("db", 4 * 19)):
+        a = open(f"{one}/random-init:7/0/{key}.mm", "rb").read()
+        b = open(f"{two}/random-init:7/0/{key}.mm", "rb").read()
+        assert len(a) == rows * 128 * 4
+        assert a == b, f"{key}.mm differs between the 1-rank and the 2-rank run"
+        assert (np.load(f"{one}/random-init:7/0/{key}_shape.npy") == np.load(f"{two}/random-init:7/0/{key}_shape.npy")).all()
+    emb = np.frombuffer(open(f"{two}/random-init:7/0/db.mm", "rb").read(), np.float32).reshape(-1, 128)
+    assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)          # no rank left its rows unwritten

@@ -128,3 +128,25 @@ def test_track_windows_cut_on_the_gpu_equal_host_cut_segments(tmp_path):
     assert got.shape == ref.shape == (seq.n_samples, 128)
     np.testing.assert_array_equal(got, ref)
     assert len(pcm) < 0.6 * rows.size
+
+
+def test_melspec_maxnorm_feature_branch(ctx, models):
+    """MODEL.FEAT = 'melspec_maxnorm' (melspectrogram.py:110-111): x = (x - min/2) / |min/2 + 1e-10| over the batch
+    tensor after the max subtraction and the clamp -- standalone log-mel and through the fused test_step."""
+    from nafp_b200.model.fp import FingerPrinter, Melspec
+    from oracle import fingerprinter as ofp
+    from oracle import melspec
+    _, _, w = models
+    x = _audio(23, seed=4)
+    x[5] = 0.0
+    ref = melspec.melspec_layer(x[:, None, :], group_size=10, segment_norm=True)          # groups 10, 10, 3
+    got = Melspec(ctx, segment_norm=True)(x[:, None, :], group_size=10)
+    assert np.abs(got - ref).max() < 1e-4
+    assert abs(got[:10].min() + 1.0) < 1e-5 and abs(got[:10].max() - 1.0) < 1e-5          # the branch maps [min, 0] to [-1, 1]
+    m_fp = FingerPrinter(ctx, segment_norm=True).load(w)
+    emb = m_fp.fingerprint(x, group_size=10)
+    eref = ofp.fingerprinter(ref, w)
+    assert (emb * eref).sum(1).min() >= 0.9999 and np.abs(emb - eref).max() <= 1e-3
+    # and the default feature is untouched by it
+    plain = Melspec(ctx)(x[:, None, :], group_size=10)
+    assert np.abs(plain - melspec.melspec_layer(x[:, None, :], group_size=10)).max() < 1e-4

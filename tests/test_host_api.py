@@ -119,3 +119,18 @@ def test_weights_roundtrip(tmp_path):
     assert w["ln0_a_g"].shape == (256, 16, 128) and w["div_w1"].shape == (128, 8, 32)
     # glorot_uniform bound of Keras for conv1_b: sqrt(6 / (3*128 + 3*128))
     assert np.abs(w["conv1_b_w"]).max() <= np.sqrt(6 / 768) + 1e-7
+
+
+def test_generate_reads_the_launcher_environment(monkeypatch):
+    """run.py generate under torchrun: rank / world / GPU come from RANK, WORLD_SIZE, LOCAL_RANK (NAFP_DEVICE overrides)."""
+    from nafp_b200.model import generate as G
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "NAFP_DEVICE"):
+        monkeypatch.delenv(k, raising=False)
+    assert G.distributed_env() == (0, 1, 0)
+    monkeypatch.setenv("RANK", "3"); monkeypatch.setenv("WORLD_SIZE", "8"); monkeypatch.setenv("LOCAL_RANK", "3")
+    assert G.distributed_env() == (3, 8, 3)
+    monkeypatch.setenv("NAFP_DEVICE", "0")
+    assert G.distributed_env() == (3, 8, 0)
+    G._barrier_fn(1)()                                  # single rank: no process group is touched
+    with pytest.raises(ValueError):
+        G.generate_fingerprint({}, 'random-init', None, None, None, True, rank=2, world_size=2)
