@@ -44,7 +44,8 @@ def select_rows(n, cnt, seed):
 
 
 def kmeans_batched(x, k, seeds, niter=25, chunk=8192):
-    """G independent k-means problems at once: x (G, n, d) -> centroids (G, k, d) float32.  Lloyd iterations from a
+    """G independent k-means problems at once: x (G, n, d) -> centroids ((G, k, d) float32 centroids, summed
+    objective per iteration).  Lloyd iterations from a
     seeded choice of k training points per problem (``select_rows``); squared distances |c|^2 - 2 x.c in float64
     (the |x|^2 term does not change the arg-min), assignment ties to the lower id, centroid = float64 mean of its
     points, empty clusters keep their centroid.  torch-CPU (all host threads); chunked over the points."""
@@ -54,26 +55,33 @@ def kmeans_batched(x, k, seeds, niter=25, chunk=8192):
     cent = torch.stack([x[g, torch.from_numpy(select_rows(n, k, int(seeds[g]))[np.arange(k) % max(min(n, k), 1)])]
                         for g in range(G)])                                   # (G, k, d)
     offs = (torch.arange(G) * k)[:, None]
+    x2 = (x * x).sum(2)                                                       # only for the reported objective
+    obj = []
     for _ in range(niter):
         c2 = (cent * cent).sum(2)                                             # (G, k)
         sums = torch.zeros((G * k, d), dtype=torch.float64)
         cnt = torch.zeros(G * k, dtype=torch.float64)
+        tot = 0.0
         for s0 in range(0, n, chunk):
             xb = x[:, s0:s0 + chunk]                                          # (G, b, d)
             dist = c2[:, None, :] - 2.0 * torch.bmm(xb, cent.transpose(1, 2))
-            a = dist.argmin(2) + offs                                         # first (lowest) index among equal minima
+            val, a = dist.min(2)                                              # first (lowest) index among equal minima
+            tot = tot + float((val + x2[:, s0:s0 + chunk]).sum())
+            a = a + offs
             sums.index_add_(0, a.reshape(-1), xb.reshape(-1, d))
             cnt.index_add_(0, a.reshape(-1), torch.ones(a.numel(), dtype=torch.float64))
         nz = cnt > 0
         new = cent.reshape(G * k, d).clone()
         new[nz] = sums[nz] / cnt[nz, None]
         cent = new.reshape(G, k, d)
-    return cent.float().numpy()
+        obj.append(tot)
+    return cent.float().numpy(), obj
 
 
 def kmeans(x, k, niter=25, seed=1234):
-    """One k-means problem (see ``kmeans_batched``); returns (centroids (k, d) float32, None)."""
-    return kmeans_batched(np.asarray(x, np.float32)[None], k, [seed], niter)[0], None
+    """One k-means problem (see ``kmeans_batched``); returns (centroids (k, d) float32, objective per iteration)."""
+    cent, obj = kmeans_batched(np.asarray(x, np.float32)[None], k, [seed], niter)
+    return cent[0], obj
 
 
 class IVFPQ:
@@ -102,7 +110,7 @@ class IVFPQ:
         self.coarse, _ = kmeans(x, self.nlist, seed=seed + 1)
         r = x - self.coarse[self._assign(x)]
         sub = np.ascontiguousarray(r.reshape(len(r), self.m, self.dsub).transpose(1, 0, 2))     # (m, n, dsub)
-        self.pq = kmeans_batched(sub, self.ksub, [seed + 2 + j for j in range(self.m)])
+        self.pq, _ = kmeans_batched(sub, self.ksub, [seed + 2 + j for j in range(self.m)])
         self.is_trained = True
 
     def _assign(self, x):
