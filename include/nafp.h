@@ -100,6 +100,12 @@ int nafp_weights_load(nafp_ctx* ctx, const float* const* conv_w, const float* co
 int nafp_logmel_forward(nafp_ctx* ctx, const float* x_dev, int64_t n_seg, int64_t group_size,
                         float* mel_dev);
 
+/* The same without the finishing pass: raw log10(mel + 0.06) and the per-group maxima (int32 per group: the float
+ * maximum in an order-preserving integer encoding; may be NULL) -- what the fused nafp_fingerprint path hands to the
+ * encoder's first layer, which applies "- max, clamp -80" itself.  Timed by bench.py for the log-mel roofline. */
+int nafp_logmel_forward_raw(nafp_ctx* ctx, const float* x_dev, int64_t n_seg, int64_t group_size,
+                            float* mel_dev, int32_t* group_max_dev);
+
 /* MODEL.FEAT (config/default.yaml:38): enable != 0 selects 'melspec_maxnorm' = Melspec_layer(segment_norm=True)
  * (melspectrogram.py:110-111: x = (x - min/2) / |min/2 + 1e-10| over the batch tensor, after the max subtraction and
  * the clamp) for nafp_logmel_forward and the nafp_fingerprint* entry points of this ctx; 0 (default) = 'melspec'. */

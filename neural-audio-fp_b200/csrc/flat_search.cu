@@ -104,29 +104,32 @@ __global__ void flat_prep_kernel(const float* __restrict__ q_all, const int32_t*
 // ------------------------------------------------------------------------------------------
 // the scan
 // ------------------------------------------------------------------------------------------
-constexpr int RING_SLOTS = 4;                           // K-block slots of the DB ring
+constexpr int RING_SLOTS = 6;                           // K-block slots of the DB ring: three 64 KB tiles in flight
 constexpr int EPI_WARPS = 16;
 constexpr int SCAN_THREADS = (3 + EPI_WARPS) * 32;   // warps 0..15 epilogue, 16 reducer, 17 TMA, 18 MMA (+TMEM alloc)
 constexpr int TMA_WARP = EPI_WARPS + 1, MMA_WARP = EPI_WARPS + 2;   // (warp EPI_WARPS is the reducer.)  The SM's warp arbiter
                                                      // favours high warp ids: the MMA issuer must never wait for a slot
-constexpr int EPI_PARTS = EPI_WARPS / 4;          // the 4 warps of a TMEM lane quadrant split the tile's 256 DB rows
-constexpr int PART_COLS = SCAN_TILE / EPI_PARTS;  // 64 DB rows (accumulator columns) per warp per unit
+constexpr int EPI_PARTS = EPI_WARPS / 4;          // the 4 warps of a TMEM lane quadrant split the unit's 128 DB rows
+constexpr int UNIT_ROWS = TILE_ROWS;              // a unit = (128-row half of a tile, 128-query half): one N = 128 accumulator
+constexpr int PART_COLS = UNIT_ROWS / EPI_PARTS;  // 32 DB rows (accumulator columns) per warp per unit
+constexpr int ACC_BUFS = 3;                       // accumulators in flight: 3 x 128 TMEM columns
+constexpr int TMEM_Q = ACC_BUFS * UNIT_ROWS;      // the query operand lives in TMEM columns [384, 512): 2 halves x 64
 constexpr int SLOT_BYTES = SCAN_TILE * 128;                // 32 KB: one 64-column K block of a 256-row tile
 constexpr int BOX_BYTES = TILE_ROWS * 128;                 // 16 KB per TMA box (128 rows)
-constexpr int Q_KB_BYTES = NQ_MAX * 128;                   // 32 KB: one K block of the query operand
-constexpr int Q_BYTES_MAX = 2 * Q_KB_BYTES;                // 64 KB
-constexpr int H_RING = 4;                               // tiles of 0.5|x|^2 kept in shared memory
+constexpr int H_RING = 8;                               // tiles of 0.5|x|^2 kept in shared memory (the producer runs up to
+                                                        // three tiles ahead of the MMAs, which run up to three units ahead of the epilogue)
 constexpr int WARM_TILES = 8;                           // tiles every CTA scans max-only before it uses thresholds
-constexpr int SCAN_SMEM = Q_BYTES_MAX + RING_SLOTS * SLOT_BYTES + H_RING * SCAN_TILE * 4 + 2 * NQ_MAX * 4 + 256 + 1024;
+constexpr int SCAN_SMEM = RING_SLOTS * SLOT_BYTES + H_RING * SCAN_TILE * 4 + 2 * NQ_MAX * 4 + 256 + 1024;
 constexpr int NEG_INF_ORD = static_cast<int>(0x807FFFFFu);  // f2ord(-inf)
-static_assert(PART_COLS == 64, "epilogue reads two 32-column chunks per unit");
+static_assert(PART_COLS == 32, "epilogue reads one 32-column chunk per unit");
+static_assert(TILE_ROWS == 128 && SCAN_TILE == 2 * TILE_ROWS, "a tile is two 128-row TMA boxes = two units per query half");
 
 struct ScanBars {
     uint64_t full[RING_SLOTS];
     uint64_t empty[RING_SLOTS];
-    uint64_t tfull[2];
-    uint64_t tempty[2];
-    uint64_t qfull;
+    uint64_t tfull[ACC_BUFS];
+    uint64_t tempty[ACC_BUFS];
+    uint64_t qfull;    // the four quadrant warps have written the query operand into TMEM
     uint32_t tmem_base;
     int done;          // epilogue warps that finished
     int tile_of[8];    // work item i (mod 8) -> DB tile, -1 = no more work (written by the TMA producer)
@@ -193,20 +196,32 @@ __device__ __forceinline__ void scan_chunk_hits(const uint32_t (&v)[32], const f
     }
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (this pass's queries) is read from tensor memory -- lane = query,
+// 32-bit column c = elements k = 2c, 2c + 1 (scripts/micro/tmem_a_test.cu) -- so an MMA reads only the DB operand from
+// shared memory (64 instead of 96 B/clk: with the TMA fill and the epilogue's traffic the 128 B/clk of shared-memory
+// bandwidth were what held the tensor pipe at 75 %) and the 64 KB the query tile took go to the DB ring.
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Orientation: the MMA's M side (TMEM lanes) are the QUERIES, its N side (accumulator columns) the
 // DB rows of the tile.  An epilogue thread therefore owns one query per 128-query half: its
 // threshold is ONE register, and the hot loop is a 3-input max over the columns followed by a single
 // compare -- no per-score add, no threshold traffic.  -0.5|x|^2 enters the prefilter through the
 // minimum over the warp's 64 rows and is applied exactly only to the few scores that pass it.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+flat_scan_kernel(const __nv_bfloat16* __restrict__ qbf, const __grid_constant__ CUtensorMap tmap_db,
                  const float* __restrict__ hn, int32_t* __restrict__ tile_counter, int64_t n_search, int n_tiles, int nq,
                  int n_half, int kg, int32_t* __restrict__ Mx, int32_t* __restrict__ Tg, uint64_t* __restrict__ pool,
                  int32_t* __restrict__ cnt, int32_t* __restrict__ flags, int32_t* __restrict__ dbg_first, int tune) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_s = smem;                                   // [kb 2][256 query rows][128 B]
-    uint8_t* b_s = smem + Q_BYTES_MAX;                     // [slot][256 DB rows][128 B]
+    uint8_t* b_s = smem;                                   // [slot][256 DB rows][128 B]
     float* h_s = reinterpret_cast<float*>(b_s + RING_SLOTS * SLOT_BYTES);     // [H_RING][256] 0.5|x|^2 of the tile's rows
     int* lmax_s = reinterpret_cast<int*>(h_s + H_RING * SCAN_TILE);
     int* cnt_s = lmax_s + NQ_MAX;
@@ -230,17 +245,16 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         cnt_s[i] = 0;
     }
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_db);
         for (int s = 0; s < RING_SLOTS; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < ACC_BUFS; ++a) {
             mbar_init(&bars->tfull[a], 1);
             mbar_init(&bars->tempty[a], EPI_WARPS);
         }
-        mbar_init(&bars->qfull, 1);
+        mbar_init(&bars->qfull, 4);
         bars->done = 0;
         mbar_fence_init();
     }
@@ -256,11 +270,6 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            const int q_rows = n_half * 128;
-            mbar_arrive_expect_tx(&bars->qfull, 2u * q_rows * 128u);
-            for (int kb = 0; kb < 2; ++kb)
-                for (int r0 = 0; r0 < q_rows; r0 += 32)
-                    tma_load_2d(q_s + kb * Q_KB_BYTES + r0 * 128, &tmap_q, &bars->qfull, kb * 64, r0);
             int tile = cta;
             int revisit = -1;                                   // >= 0: index of the warm tile being revisited
             int nxt = warm * G + atomicAdd(tile_counter, 1);    // drawn one item ahead: the round trip hides behind the loads
@@ -302,66 +311,89 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         __syncwarp();
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------ MMA issuer
-        // unit = (tile, 128-query half): D[query][db row] in accumulator (unit & 1).  The second K block's
-        // slot is released as soon as the last unit's MMAs on it are issued, the first one's four MMAs earlier.
+        // unit = (128-row half of the tile, 128-query half): D[query][db row] in accumulator (unit % 3), N = 128.
+        // A K-block slot is released as soon as the last unit's MMAs on it are issued.
         // The whole warp runs the loop (uniform control flow keeps descriptors and counters in uniform
         // registers); one elected lane issues.
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc_f16(1u, 128u, static_cast<uint32_t>(SCAN_TILE));
-        const uint64_t adesc0 = umma_desc_sw128(smem_u32(q_s));
+        const uint32_t idesc = umma_idesc_f16(1u, 128u, static_cast<uint32_t>(UNIT_ROWS));
         const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_s));
         mbar_wait_parked(&bars->qfull, 0);
+        tc_fence_after();
         uint32_t uc = 0;
         bool more = true;
         for (int i = 0; more; ++i) {
             const int s0 = (2 * i) % RING_SLOTS, s1 = s0 + 1;
             const uint32_t ph = ((2 * i) / RING_SLOTS) & 1;
-            for (int hq = 0; hq < n_half; ++hq, ++uc) {
-                const int acc = uc & 1;
-                const uint32_t aph = (uc >> 1) & 1;
-                const bool last = hq == n_half - 1;
-                mbar_wait_parked(&bars->tempty[acc], aph ^ 1);
-                if (hq == 0) {
-                    mbar_wait_parked(&bars->full[s0], ph);
-                    if (smem_ld_volatile(&bars->tile_of[i & 7]) < 0) {      // end marker: wake the epilogue and stop
-                        if (leader) tc_commit(&bars->tfull[acc]);
-                        __syncwarp();
-                        more = false;
-                        break;
+            for (int sub = 0; sub < 2 && more; ++sub) {
+                for (int hq = 0; hq < n_half; ++hq, ++uc) {
+                    const int acc = uc % ACC_BUFS;
+                    const uint32_t aph = (uc / ACC_BUFS) & 1;
+                    const bool first = sub == 0 && hq == 0;
+                    const bool last = sub == 1 && hq == n_half - 1;
+                    mbar_wait_parked(&bars->tempty[acc], aph ^ 1);
+                    if (first) {
+                        mbar_wait_parked(&bars->full[s0], ph);
+                        if (smem_ld_volatile(&bars->tile_of[i & 7]) < 0) {      // end marker: wake the epilogue and stop
+                            if (leader) tc_commit(&bars->tfull[acc]);
+                            __syncwarp();
+                            more = false;
+                            break;
+                        }
                     }
-                }
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * SCAN_TILE;
-                const uint64_t a_kb0 = adesc0 + static_cast<uint64_t>((hq * (128 * 128)) >> 4);
-                const uint64_t a_kb1 = a_kb0 + static_cast<uint64_t>(Q_KB_BYTES >> 4);
-                const uint64_t b_kb0 = bdesc0 + static_cast<uint64_t>((s0 * SLOT_BYTES) >> 4);
-                const uint64_t b_kb1 = b_kb0 + static_cast<uint64_t>(SLOT_BYTES >> 4);
-                if (leader) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, a_kb0 + 2 * j, b_kb0 + 2 * j, idesc, j != 0 ? 1u : 0u);
-                    if (last) tc_commit(&bars->empty[s0]);
-                }
-                if (hq == 0) {
-                    mbar_wait_parked(&bars->full[s1], ph);
                     tc_fence_after();
-                }
-                if (leader) {
+                    const uint32_t d_tmem = tmem_base + acc * UNIT_ROWS;
+                    const uint32_t a_tmem = tmem_base + TMEM_Q + hq * 64;              // 128 bf16 = 64 columns per half
+                    const uint64_t b_kb0 = bdesc0 + static_cast<uint64_t>((s0 * SLOT_BYTES + sub * BOX_BYTES) >> 4);
+                    const uint64_t b_kb1 = b_kb0 + static_cast<uint64_t>(SLOT_BYTES >> 4);
+                    if (leader) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, a_kb1 + 2 * j, b_kb1 + 2 * j, idesc, 1u);
-                    if (last) tc_commit(&bars->empty[s1]);
-                    tc_commit(&bars->tfull[acc]);
+                        for (int j = 0; j < 4; ++j) tc_mma_f16_ts(d_tmem, a_tmem + 8 * j, b_kb0 + 2 * j, idesc, j != 0 ? 1u : 0u);
+                        if (last) tc_commit(&bars->empty[s0]);
+                    }
+                    if (first) {
+                        mbar_wait_parked(&bars->full[s1], ph);
+                        tc_fence_after();
+                    }
+                    if (leader) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tc_mma_f16_ts(d_tmem, a_tmem + 32 + 8 * j, b_kb1 + 2 * j, idesc, 1u);
+                        if (last) tc_commit(&bars->empty[s1]);
+                        tc_commit(&bars->tfull[acc]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         __syncwarp();
     } else if (warp < EPI_WARPS) {
         // ------------------------------------------------------------ epilogue (EPI_WARPS warps)
-        // Warp e reads TMEM lane quadrant (warp & 3) -- 32 queries per half -- and the 64 accumulator
-        // columns (DB rows) [64 part, 64 part + 64) of every unit.
+        // Warp e reads TMEM lane quadrant (warp & 3) -- 32 queries per half -- and the 32 accumulator
+        // columns (DB rows) [32 part, 32 part + 32) of every unit.
         const int qd = warp & 3;
         const int e = warp;               // 0..EPI_WARPS-1
         const int part = e >> 2;          // 0..EPI_PARTS-1
+        // ---- the query operand: the quadrant's first warp copies its 32 queries of each half (a 256-byte bf16 row per
+        // thread) from global memory into TMEM columns [TMEM_Q + 64 half, + 64) of its lanes, once per pass
+        if (part == 0) {
+            for (int hq = 0; hq < n_half; ++hq) {
+                const uint4* src = reinterpret_cast<const uint4*>(qbf + static_cast<int64_t>(hq * 128 + qd * 32 + lane) * D128);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 w = __ldg(src + c * 4 + j);
+                        v[4 * j] = w.x; v[4 * j + 1] = w.y; v[4 * j + 2] = w.z; v[4 * j + 3] = w.w;
+                    }
+                    tmem_st_32x16(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + TMEM_Q + hq * 64 + c * 16, v);
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            mbar_arrive_lane0(&bars->qfull, lane);
+        }
         constexpr int QPW = NQ_MAX / EPI_WARPS;      // queries whose maxima this warp publishes
         const float NEG_INF = -INFINITY;
         int pub = INT_MIN;
@@ -428,52 +460,53 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // running maxima from which the shared thresholds are built; they come back, with thresholds, as the
         // last items.
         for (int w = 0; w < warm; ++w) {
-            const uint32_t row0 = static_cast<uint32_t>(cta + w * G) * SCAN_TILE + part * PART_COLS;
-            const float* h_part = h_s + (w % H_RING) * SCAN_TILE + part * PART_COLS;
             // rows of (numerically) equal norm, all searchable -- fingerprints are unit vectors --: the best score of a
             // chunk is its maximum minus the common 0.5|x|^2 (FMNMX3 chain).  Otherwise (reconstructions of an
             // IVF-PQ index, raw vectors, halo / padding rows): exact, column by column.
-            bool edge = (static_cast<uint32_t>(cta + w * G) + 1u) * SCAN_TILE > ns32 || (tune & 4);
-            float hx = 0.f;
-            for (int hq = 0; hq < n_half; ++hq, ++uc) {
-                const int acc = uc & 1;
-                mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
-                if (hq == 0 && !edge) {
-                    const float a = h_part[lane], b = h_part[32 + lane];
-                    const float hmax_w = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(a, b))));
-                    const float hmin_w = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(a, b))));
-                    hx = hmax_w * (1.f + 1.f / 1048576.f);
-                    edge = !(hmax_w - hmin_w <= hmax_w * (1.f / 262144.f));
-                }
-                tc_fence_after();
-                float munit = NEG_INF;
-#pragma unroll 1
-                for (int c = 0; c < PART_COLS / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tlane + acc * SCAN_TILE + c * 32, v);
-                    tc_wait_ld();
-                    if (!edge) {
-                        float gm[4];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            float m = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
-                            m = fmax3(m, __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
-                            m = fmax3(m, __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
-                            gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
-                        }
-                        munit = fmaxf(munit, fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]) - hx);
-                    } else {
-                        const float* hc = h_part + c * 32;
-                        const int nvalid = static_cast<int>(min(ns32 - min(ns32, row0 + c * 32), 32u));   // rows < n_search
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) munit = fmaxf(munit, __uint_as_float(v[j]) - hc[j]);
+            const bool tile_edge = (static_cast<uint32_t>(cta + w * G) + 1u) * SCAN_TILE > ns32 || (tune & 4);
+            for (int sub = 0; sub < 2; ++sub) {
+                const uint32_t row0 = static_cast<uint32_t>(cta + w * G) * SCAN_TILE + sub * UNIT_ROWS + part * PART_COLS;
+                const float* h_part = h_s + (w % H_RING) * SCAN_TILE + sub * UNIT_ROWS + part * PART_COLS;
+                bool edge = tile_edge;
+                float hx = 0.f;
+                for (int hq = 0; hq < n_half; ++hq, ++uc) {
+                    const int acc = uc % ACC_BUFS;
+                    mbar_wait_parked(&bars->tfull[acc], (uc / ACC_BUFS) & 1);
+                    if (hq == 0 && !edge) {
+                        const float a = h_part[lane];
+                        const float hmax_w = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(a)));
+                        const float hmin_w = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(a)));
+                        hx = hmax_w * (1.f + 1.f / 1048576.f);
+                        edge = !(hmax_w - hmin_w <= hmax_w * (1.f / 262144.f));
                     }
+                    tc_fence_after();
+                    float munit = NEG_INF;
+                    {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tlane + acc * UNIT_ROWS, v);
+                        tc_wait_ld();
+                        if (!edge) {
+                            float gm[4];
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                float m = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                                m = fmax3(m, __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
+                                m = fmax3(m, __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
+                                gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+                            }
+                            munit = fmaxf(munit, fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]) - hx);
+                        } else {
+                            const int nvalid = static_cast<int>(min(ns32 - min(ns32, row0), 32u));   // rows < n_search
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) munit = fmaxf(munit, __uint_as_float(v[j]) - h_part[j]);
+                        }
+                    }
+                    if (hq == 0 ? active[0] : active[1]) smem_red_max(&lmax_s[hq * 128 + qd * 32 + lane], f2ord(munit));
+                    tc_fence_before();
+                    __syncwarp();
+                    mbar_arrive_lane0(&bars->tempty[acc], lane);
                 }
-                if (hq == 0 ? active[0] : active[1]) smem_red_max(&lmax_s[hq * 128 + qd * 32 + lane], f2ord(munit));
-                tc_fence_before();
-                __syncwarp();
-                mbar_arrive_lane0(&bars->tempty[acc], lane);
             }
             publish_maxima();
             if (w == 0) stamp(0);
@@ -500,64 +533,62 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // 7 M-row pass).  Loads issued now, consumed after the tile.
             const bool rf = i > warm && (((tune & 8) && i < warm + 32) || (i & 3) == 0);
             if (rf) load_thresholds(tg);
-            const float* h_part = h_s + (i % H_RING) * SCAN_TILE + part * PART_COLS;
-            uint32_t row0 = 0;
-            float hm = 0.f;
             bool end = false, edge = false;
-            for (int hq = 0; hq < n_half; ++hq, ++uc) {
-                const int acc = uc & 1;
-                mbar_wait_parked(&bars->tfull[acc], (uc >> 1) & 1);
-                if (hq == 0) {
-                    const int tile = smem_ld_volatile(&bars->tile_of[i & 7]);
-                    if (tile < 0) {
-                        end = true;
-                        break;
+            for (int sub = 0; sub < 2 && !end; ++sub) {
+                const float* h_part = h_s + (i % H_RING) * SCAN_TILE + sub * UNIT_ROWS + part * PART_COLS;
+                uint32_t row0 = 0;
+                float hm = 0.f;
+                for (int hq = 0; hq < n_half; ++hq, ++uc) {
+                    const int acc = uc % ACC_BUFS;
+                    mbar_wait_parked(&bars->tfull[acc], (uc / ACC_BUFS) & 1);
+                    if (hq == 0) {
+                        const int tile = smem_ld_volatile(&bars->tile_of[i & 7]);
+                        if (tile < 0) {
+                            end = true;
+                            break;
+                        }
+                        row0 = static_cast<uint32_t>(tile) * SCAN_TILE + sub * UNIT_ROWS + part * PART_COLS;
+                        // prefilter offset: s = v - h > T implies v > T + min(h) over this warp's 32 rows (minus a
+                        // rounding margin); the rows' 0.5|x|^2 arrived in shared memory with the tile
+                        const float hmin_w = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(h_part[lane])));
+                        hm = hmin_w * (1.f - 1.f / 1048576.f);
+                        // the tile holds rows that do not take part in the search (halo, padding)
+                        edge = (static_cast<uint32_t>(tile) + 1u) * SCAN_TILE > ns32 || (tune & 4);
                     }
-                    row0 = static_cast<uint32_t>(tile) * SCAN_TILE + part * PART_COLS;
-                    // prefilter offset: s = v - h > T implies v > T + min(h) over this warp's 64 rows (minus a
-                    // rounding margin); the rows' 0.5|x|^2 arrived in shared memory with the tile
-                    const float hmin_w =
-                        __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fminf(h_part[lane], h_part[32 + lane]))));
-                    hm = hmin_w * (1.f - 1.f / 1048576.f);
-                    // the tile holds rows that do not take part in the search (halo, padding)
-                    edge = (static_cast<uint32_t>(tile) + 1u) * SCAN_TILE > ns32 || (tune & 4);
-                }
-                const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
-                tc_fence_after();
-                const uint32_t taddr = tlane + acc * SCAN_TILE;
-#pragma unroll 1
-                for (int c = 0; c < PART_COLS / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c * 32, v);
-                    tc_wait_ld();
-                    // maxima of the four 8-column groups (FMNMX3), then of the chunk
-                    float gm[4];
+                    const float tp = (hq == 0 ? t_pre[0] : t_pre[1]) + hm;
+                    tc_fence_after();
+                    {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tlane + acc * UNIT_ROWS, v);
+                        tc_wait_ld();
+                        // maxima of the four 8-column groups (FMNMX3), then of the chunk
+                        float gm[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float m = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
-                        m = fmax3(m, __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
-                        m = fmax3(m, __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
-                        gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+                        for (int g = 0; g < 4; ++g) {
+                            float m = fmax3(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]));
+                            m = fmax3(m, __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]));
+                            m = fmax3(m, __uint_as_float(v[8 * g + 5]), __uint_as_float(v[8 * g + 6]));
+                            gm[g] = fmaxf(m, __uint_as_float(v[8 * g + 7]));
+                        }
+                        const float ma = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
+                        const bool fired = ma > tp;
+                        if (__any_sync(0xffffffffu, fired)) {
+                            // rare -- except in the first thresholded tiles of a pass, while the thresholds are still
+                            // loose (an event per warp per tile): see scan_chunk_hits
+                            const int q = hq * 128 + qd * 32 + lane;
+                            const float te = hq == 0 ? t_exact[0] : t_exact[1];
+                            if (!edge)
+                                scan_chunk_hits<false>(v, h_part, te, 32, row0, &cnt_s[q], &lmax_s[q], my_pool + q * POOL_CAP);
+                            else
+                                scan_chunk_hits<true>(v, h_part, te, static_cast<int>(min(ns32 - min(ns32, row0), 32u)), row0,
+                                                      &cnt_s[q], &lmax_s[q], my_pool + q * POOL_CAP);
+                            __syncwarp();
+                        }
                     }
-                    const float ma = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
-                    const bool fired = ma > tp;
-                    if (__any_sync(0xffffffffu, fired)) {
-                        // rare -- except in the first thresholded tiles of a pass, while the thresholds are still
-                        // loose (an event per warp per tile): see scan_chunk_hits
-                        const int q = hq * 128 + qd * 32 + lane;
-                        const float te = hq == 0 ? t_exact[0] : t_exact[1];
-                        const uint32_t rbase = row0 + c * 32;
-                        if (!edge)
-                            scan_chunk_hits<false>(v, h_part + c * 32, te, 32, rbase, &cnt_s[q], &lmax_s[q], my_pool + q * POOL_CAP);
-                        else
-                            scan_chunk_hits<true>(v, h_part + c * 32, te, static_cast<int>(min(ns32 - min(ns32, rbase), 32u)), rbase,
-                                                  &cnt_s[q], &lmax_s[q], my_pool + q * POOL_CAP);
-                        __syncwarp();
-                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    mbar_arrive_lane0(&bars->tempty[acc], lane);
                 }
-                tc_fence_before();
-                __syncwarp();
-                mbar_arrive_lane0(&bars->tempty[acc], lane);
             }
             if (end) break;
             if (rf) apply_thresholds(tg, i);
@@ -993,11 +1024,6 @@ static int ensure_scratch(nafp_index* idx) {
     NAFP_CUDA(cudaMalloc(&idx->stats, 8 * sizeof(unsigned long long)));
     NAFP_CUDA(cudaMalloc(&idx->tile_counter, sizeof(int32_t)));
     NAFP_CUDA(cudaMemsetAsync(idx->stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    const uint64_t dims[2] = {static_cast<uint64_t>(D128), static_cast<uint64_t>(NQ_MAX)};
-    const uint64_t strides[2] = {2, static_cast<uint64_t>(D128) * 2};
-    const uint32_t box[2] = {64, 32};
-    NAFP_TRY(make_tensor_map(&idx->tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, idx->qbf, dims, strides, box, nullptr,
-                             CU_TENSOR_MAP_SWIZZLE_128B));
     NAFP_CUDA(cudaFuncSetAttribute(flat_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
     idx->scratch_ready = true;
     return NAFP_OK;
@@ -1043,7 +1069,7 @@ static int scan_pass(nafp_index* idx, const float* q_dev, const int32_t* src_lis
                                                                          idx->qbf, q32, qn2, idx->Mx, Tg, flags, gidx, idx->tile_counter);
     const bool prof = idx->profile && idx->prof_n < PROF_RING;
     if (prof) cudaEventRecord(idx->prof_ev[2 * idx->prof_n], ctx->stream);
-    flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->tmap_q, idx->tmap_db, idx->hn, idx->tile_counter, n_search,
+    flat_scan_kernel<<<grid_scan, SCAN_THREADS, SCAN_SMEM, ctx->stream>>>(idx->qbf, idx->tmap_db, idx->hn, idx->tile_counter, n_search,
                                                                           n_tiles, np, n_half, kg, idx->Mx, Tg, pool, cnt, flags,
                                                                           idx->dbg_first, scan_tune());
     if (prof) {

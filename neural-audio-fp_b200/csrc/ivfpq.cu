@@ -97,9 +97,9 @@ __global__ void kmeans_assign_kernel(const float* __restrict__ x, int64_t n, int
     for (int c = lane; c < k; c += 32) {
         const float* cr = cent + static_cast<int64_t>(c) * dim;
         float d = 0.f;
-        for (int j = 0; j < dim; ++j) {
+        for (int j = 0; j < dim; ++j) {        // d = fma(t, t, d), j ascending: the oracle's k-means (oracle.c) rounds identically
             const float t = xr[j] - __ldg(cr + j);
-            d += t * t;
+            d = fmaf(t, t, d);
         }
         if (d < best) { best = d; bi = c; }
     }

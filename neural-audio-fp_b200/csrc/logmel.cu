@@ -388,3 +388,19 @@ extern "C" int nafp_logmel_forward(nafp_ctx* ctx, const float* x_dev, int64_t n_
     NAFP_REQUIRE(ctx, NAFP_ERR_INVALID, "nafp_logmel_forward: ctx is NULL");
     return nafp::logmel_run(ctx, x_dev, false, n_seg, group_size, mel_dev, true, nullptr, nullptr, nullptr);
 }
+
+/* The log-mel kernel alone, as the fused extractor runs it: raw log10(mel + 0.06) + the per-group maxima (ordered-int
+ * encoding of the float maximum; NULL to skip the copy); the "- max, clamp" of melspectrogram.py:108-109 is then applied by
+ * the encoder's first layer.  bench.py times this entry for the log-mel roofline (64,768 algorithmic bytes per segment). */
+extern "C" int nafp_logmel_forward_raw(nafp_ctx* ctx, const float* x_dev, int64_t n_seg, int64_t group_size, float* mel_dev,
+                                       int32_t* group_max_dev) {
+    NAFP_RANGE("nafp_logmel_forward_raw");
+    NAFP_REQUIRE(ctx, NAFP_ERR_INVALID, "nafp_logmel_forward_raw: ctx is NULL");
+    NAFP_REQUIRE(!nafp::logmel_segment_norm(ctx), NAFP_ERR_STATE, "nafp_logmel_forward_raw: melspec_maxnorm needs the finishing pass");
+    const int32_t* gmax = nullptr;
+    NAFP_TRY(nafp::logmel_run(ctx, x_dev, false, n_seg, group_size, mel_dev, false, &gmax, nullptr, nullptr));
+    if (group_max_dev && n_seg > 0)
+        NAFP_CUDA(cudaMemcpyAsync(group_max_dev, gmax, static_cast<size_t>((n_seg + group_size - 1) / group_size) * sizeof(int32_t),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    return NAFP_OK;
+}

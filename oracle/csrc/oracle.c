@@ -130,19 +130,22 @@ int orc_flat_search(const float* q, int64_t nq, const float* x, int64_t n, int d
 }
 
 /* ---------------------------------------------------------------- k-means (Lloyd) */
-/* nearest centroid of every point: squared distances accumulated in double, ties to the lower centroid id */
+/* nearest centroid of every point, ties to the lower centroid id.  The squared distance is DEFINED as the fp32 chain
+ * s = fma(t, t, s), t = x_j - c_j, j ascending (faiss computes fp32 distances as well): k-means amplifies every
+ * flipped assignment over its 25 iterations, so the CUDA implementation (csrc/ivfpq.cu kmeans_assign_kernel) and this
+ * one only train the same quantizers if they round the same way. */
 static void assign_points(const float* x, int64_t n, int ld, int d, const float* cent, int k, int32_t* assign) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         const float* xr = x + i * ld;
-        double best = DBL_MAX;
+        float best = FLT_MAX;
         int bi = 0;
         for (int c = 0; c < k; ++c) {
             const float* cr = cent + (int64_t)c * d;
-            double s = 0.0;
+            float s = 0.f;
             for (int j = 0; j < d; ++j) {
-                const double t = (double)xr[j] - (double)cr[j];
-                s += t * t;
+                const float t = xr[j] - cr[j];
+                s = fmaf(t, t, s);
             }
             if (s < best) { best = s; bi = c; }
         }

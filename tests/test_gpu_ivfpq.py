@@ -76,31 +76,53 @@ def test_ivfpq_fallback_and_fast_path_agree_with_oracle(nprobe, k):
         assert Ig[r, c] in Io[r] or abs(Dg[r, c] - Do[r, min(c + 1, k - 1)]) < 2e-5 or abs(Dg[r, c] - Do[r, c]) < 2e-5
 
 
-def test_ivfpq_training_quality_and_hit_rate():
-    """Own k-means on the GPU vs the oracle's own k-means: quantisation error and top-1 recall agree."""
+def test_ivfpq_own_training_hit_rate_within_a_tenth_of_a_point():
+    """The IVF-PQ gate of north_star -- top-1 hit rate within 0.1 pt of the reference index -- at a scale where 0.1 pt
+    is resolvable: 200,000 + 2,360 rows, 2,360 query rows, three training seeds, BOTH sides running their OWN k-means
+    (GPU: csrc/ivfpq.cu; oracle: the C restatement oracle/csrc/oracle.c) on the same seeded training subset.
+    Measured: segment-level top-1 recall against the exact search and sequence-level top-1 hit rate of the
+    evaluation loop; the averages over the seeds must agree to 0.1 pt, every single seed to 0.3 pt."""
     from nafp_b200 import synth
     from nafp_b200.eval.utils.get_index import IVFPQ, Index
-    from oracle.flat_index import FlatL2
-    from oracle.ivfpq_index import IVFPQ as OracleIVFPQ
-    dummy, db, query = synth.synth_search_set(20000, 590, seed=8)
-    g = Index(IVFPQ, 128, nlist=64, pq_m=64, pq_nbits=8)
-    g.train(dummy)
-    g.add(dummy)
-    g.add(db)
-    g.nprobe = 16
-    o = OracleIVFPQ(128, 64, 64, 8)
-    o.train(dummy)
-    o.add(dummy)
-    o.add(db)
-    o.nprobe = 16
-    flat = FlatL2(128)
+    from oracle import native, seq_match
+    dummy, db, query = synth.synth_search_set(200_000, 2360, seed=31)
+    recon = np.concatenate([dummy, db])
+    flat = native.FlatL2C(128)
     flat.add(dummy)
     flat.add(db)
-    _, Ie = flat.search(query[:200], 1)
-    _, Ig = g.search(query[:200], 20)
-    _, Io = o.search(query[:200], 20)
-    rg, ro = (Ig[:, 0] == Ie[:, 0]).mean(), (Io[:, 0] == Ie[:, 0]).mean()
-    assert abs(rg - ro) <= 0.12 and rg >= 0.6, (rg, ro)       # different seeds of the same k-means: a few points apart
+    _, Ie = flat.search(query, 1)
+    ids = np.arange(0, 2360 - 19, 4)                       # 586 sequences x 3 lengths
+    lens = [1, 3, 5]
+    gt = ids + len(dummy)
+    rec, hit = [], []
+    for seed in (1234, 7, 99):
+        g = Index(IVFPQ, 128, nlist=256, pq_m=64, pq_nbits=8)
+        g.train(dummy[:100_000], seed=seed)
+        g.add(dummy)
+        g.add(db)
+        g.nprobe = 40
+        o = native.IVFPQC(128, 256, 64, 8)
+        o.train(dummy[:100_000], seed=seed)
+        o.add(dummy)
+        o.add(db)
+        o.nprobe = 40
+        cg, pg = g.ivfpq_params()
+        # same algorithm, same rows, same fp32 rounding of the assignment distances: the two trainings agree
+        print("seed", seed, "mean |coarse diff|", float(np.abs(cg - o.coarse).mean()), "mean |pq diff|", float(np.abs(pg - o.pq).mean()))
+        assert np.abs(cg - o.coarse).mean() < 1e-2 and np.abs(pg - o.pq).mean() < 2e-2
+        _, Ig = g.search(query, 20)
+        _, Io = o.search(query, 20)
+        rec.append(((Ig[:, 0] == Ie[:, 0]).mean(), (Io[:, 0] == Ie[:, 0]).mean()))
+        pred_g, _ = g.seq_match(query, ids, lens, 20)
+        _, pred_o = seq_match.evaluate(o, query, recon, len(dummy), ids, lens, 20, fast_scores=True, batch_search=True)
+        hit.append(((pred_g[:, :, 0] == gt[:, None]).mean(0), (pred_o[:, :, 0] == gt[:, None]).mean(0)))
+        del g
+    rec, hit = np.array(rec), np.array(hit)
+    print("segment top-1 recall (gpu, oracle) per seed:", rec.tolist())
+    print("sequence top-1 hit rate (gpu, oracle) per seed:", hit.tolist())
+    assert 0.5 < rec[:, 1].mean() < 0.999                  # the approximation is visible: the comparison means something
+    assert np.abs(rec[:, 0] - rec[:, 1]).max() <= 0.003 and abs(rec[:, 0].mean() - rec[:, 1].mean()) <= 0.001
+    assert np.abs(hit[:, 0] - hit[:, 1]).max() <= 0.003 and np.abs(hit[:, 0].mean(0) - hit[:, 1].mean(0)).max() <= 0.001
 
 
 def test_ivfpq_untrained_add_is_refused():

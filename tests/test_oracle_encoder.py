@@ -84,3 +84,20 @@ def test_golden_extractor_fingerprint():
     w = weights.init_weights(7, randomize_affine=True)
     e = ofp.fingerprinter(g["mel"][..., None], w)
     assert np.abs(e - g["emb"]).max() < 2e-6
+
+
+def test_torch_cpu_extractor_equals_the_fp64_oracle():
+    """oracle/torch_ref.py (the TIMED torch-CPU form used as the generation cpu_baseline) == the parity oracles."""
+    from nafp_b200 import synth
+    from nafp_b200.model import weights as W
+    from oracle import fingerprinter as ofp
+    from oracle import melspec, torch_ref
+    w = W.init_weights(7, randomize_affine=True)
+    tr = synth.synth_track(3).astype(np.float32) / 32768
+    x = np.stack([tr[i * 4000:i * 4000 + 8000] for i in range(7)])[:, None, :]
+    m_ref = melspec.melspec_layer(x, group_size=4)
+    m_t = torch_ref.melspec_torch(x, group_size=4)
+    assert m_t.shape == m_ref.shape and np.abs(m_t - m_ref).max() < 1e-5
+    e_ref = ofp.fingerprinter(m_ref, w)
+    e_t = torch_ref.TorchFingerPrinter(w)(m_t)
+    assert np.abs(e_t - e_ref).max() < 1e-5 and (e_t * e_ref).sum(1).min() > 0.999999

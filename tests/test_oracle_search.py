@@ -75,3 +75,22 @@ def test_golden_search_fixture():
     assert (I == g["I"]).all() and np.abs(D - g["D"]).max() < 1e-6
     raw, pred = seq_match.evaluate(idx, query, np.concatenate([dummy, db]), len(dummy), g["test_ids"], list(g["seq_lens"]), 20)
     assert (raw == g["raw"]).all() and (pred == g["pred"]).all()
+
+
+def test_scalable_matcher_forms_equal_the_literal_loop():
+    """oracle.seq_match.evaluate(fast_scores=True, batch_search=True) -- the forms bench.py times / runs at scale --
+    give the predictions and hit flags of the literal restatement of eval_faiss.py:204-243."""
+    from nafp_b200 import synth
+    from oracle import native, seq_match
+    from oracle.flat_index import FlatL2
+    dummy, db, query = synth.synth_search_set(6000, 590, seed=21)
+    o, c = FlatL2(128), native.FlatL2C(128)
+    for idx in (o, c):
+        idx.add(dummy)
+        idx.add(db)
+    recon = np.concatenate([dummy, db])
+    ids = np.r_[np.arange(0, 560, 11), 585]                  # 585 + 19 runs past the end of the query set
+    r1, p1 = seq_match.evaluate(o, query, recon, len(dummy), ids, [1, 3, 9, 19], 20)
+    r2, p2 = seq_match.evaluate(c, query, recon, len(dummy), ids, [1, 3, 9, 19], 20, fast_scores=True)
+    r3, p3 = seq_match.evaluate(c, query, recon, len(dummy), ids, [1, 3, 9, 19], 20, fast_scores=True, batch_search=True)
+    assert (p1 == p2).all() and (p1 == p3).all() and (r1 == r2).all() and (r1 == r3).all()
