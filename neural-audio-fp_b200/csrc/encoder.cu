@@ -106,7 +106,7 @@ struct EncoderState {
                                                // with the loads for the same TMA / L2 request slots; kept as a switch)
     int64_t last_n = 0;                        // segments of the last pass (activation probe)
 };
-constexpr int PART_SLOTS = 256;                // most partial-sum slots per segment of any layer (L1b: 64 groups x 4 parts)
+constexpr int PART_SLOTS = 256;                // most partial-sum slots per segment of any layer (L1b: 64 groups x <= 4 parts)
 
 static const int kHidden[8] = {128, 128, 256, 256, 512, 512, 1024, 1024};      // nnfp.py:193
 static const int kStrideT[8] = {2, 2, 2, 2, 1, 2, 1, 2};                        // nnfp.py:194-197 (1x3 conv)
@@ -308,7 +308,10 @@ ln_stats_kernel(const float* __restrict__ part, int slots, int per_seg, int n_se
 //                re-streamed for every M tile), which the wider tile cuts by 25 %; their parameters repeat every
 //                `ms` rows and are read per tile through L1 (<= 9 % of the operand bytes).
 constexpr int CONV_MAX_STAGES = 6;
-constexpr int CONV_EPI_WARPS = 16;         // 4 per TMEM lane quadrant: each takes a quarter of the tile's columns
+#ifndef NAFP_CONV_EPI_WARPS
+#define NAFP_CONV_EPI_WARPS 8      // measured: 5.65 ms per 4,000 segments with 8 warps (152 registers, two chunks of TMEM loads
+#endif                             // in flight per warp) against 5.99 ms with 16 (96 registers, spills)
+constexpr int CONV_EPI_WARPS = NAFP_CONV_EPI_WARPS;      // 4 (or 2) per TMEM lane quadrant: each takes a share of the tile's columns
 constexpr int CONV_EPI_PARTS = CONV_EPI_WARPS / 4;
 constexpr int CONV_THREADS = (2 + CONV_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2.. epilogue
 constexpr int CONV_A_BYTES = 128 * 128;    // 128 rows x 64 fp16
@@ -512,30 +515,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // this thread's (position, CPW channels) of the per-element constants
         const int pos = p.ms >= 128 ? ptile * 128 + r : r % p.ms;
         const int64_t poff = static_cast<int64_t>(pos) * p.c_out + n_base;
-        uint32_t cg[STATIONARY ? 16 : 1];      // half2 pairs
+        uint32_t cg[STATIONARY ? CPW / 2 : 1];      // half2 pairs
         if constexpr (STATIONARY) {
             // ---- stationary: gamma and Cb into the free TMEM columns, Cg into registers, once per launch
             const uint4* gs = reinterpret_cast<const uint4*>(gamma + poff);
             const uint4* bs = reinterpret_cast<const uint4*>(cbeta + poff);
             const uint4* cs = reinterpret_cast<const uint4*>(cgam + poff);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < CPW / 16; ++h) {
                 uint32_t v[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint4 q = __ldg(gs + h * 4 + j);
                     v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
                 }
-                tmem_st_32x16(lane_base + TMEM_GAMMA + cpart * 32 + h * 16, v);
+                tmem_st_32x16(lane_base + TMEM_GAMMA + cpart * CPW + h * 16, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint4 q = __ldg(bs + h * 4 + j);
                     v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
                 }
-                tmem_st_32x16(lane_base + TMEM_CBETA + cpart * 32 + h * 16, v);
+                tmem_st_32x16(lane_base + TMEM_CBETA + cpart * CPW + h * 16, v);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CPW / 8; ++j) {            // 8 fp16 values per 16-byte load
                 const uint4 q = __ldg(cs + j);
                 cg[4 * j] = q.x; cg[4 * j + 1] = q.y; cg[4 * j + 2] = q.z; cg[4 * j + 3] = q.w;
             }
@@ -578,8 +581,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t va[16], vg[16], vb[16], cgl[8];
                 tmem_ld_32x16(lane_base + acc * NTILE + cpart * CPW + h * 16, va);
                 if constexpr (STATIONARY) {
-                    tmem_ld_32x16(lane_base + TMEM_GAMMA + cpart * 32 + h * 16, vg);
-                    tmem_ld_32x16(lane_base + TMEM_CBETA + cpart * 32 + h * 16, vb);
+                    tmem_ld_32x16(lane_base + TMEM_GAMMA + cpart * CPW + h * 16, vg);
+                    tmem_ld_32x16(lane_base + TMEM_CBETA + cpart * CPW + h * 16, vb);
                 } else {
                     // per tile through L1: the tile's rows repeat every ms positions and the next tile reads the same lines
                     const uint4* gs = reinterpret_cast<const uint4*>(gamma + poff + h * 16);
@@ -604,7 +607,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (lane == 0) mbar_arrive(&bars->tempty[acc]);
                 }
                 uint32_t hi[8], lo[8];
-                conv_epi_chunk(va, vg, vb, STATIONARY ? &cg[(h & 1) * 8] : cgl, sta, stc, split, ps1, ps2, hi, lo);
+                // (loading chunk h + 1 while chunk h is computed was measured slower: 7.07 vs 6.26 ms per 4,000 segments)
+                conv_epi_chunk(va, vg, vb, STATIONARY ? &cg[(STATIONARY ? h : 0) * 8] : cgl, sta, stc, split, ps1, ps2, hi, lo);
                 if (row_ok) {
                     uint4* dst = reinterpret_cast<uint4*>(xrow + h * 16);
                     dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

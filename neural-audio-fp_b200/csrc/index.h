@@ -36,6 +36,7 @@ struct nafp_index {
     int64_t label_offset = 0;
     int64_t search_rows = -1;     // leading rows that take part in search (-1 = all); the rest are halo
     CUtensorMap tmap_db;
+    CUtensorMap tmap_q;
     bool tmap_db_valid = false;
 
     // per-pass scratch (allocated on first search); q32 .. gidx hold SEL_SLOTS passes

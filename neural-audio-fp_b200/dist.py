@@ -74,7 +74,14 @@ def sharded_seq_match(ops, comm, query, test_ids, seq_lens, k_probe):
         I = I_loc
     cand_ids, cand_scores, n_cand = ops.cand_scores(query, plan, test_ids, seq_lens, k_probe, I)
     if comm is not None:
-        cand_scores = comm.all_reduce_max(cand_scores)
+        # a test id has at most k_probe x max_len distinct candidates (380 of the table's 1,024 columns at k_probe 20,
+        # length 19): only that part of the score table is live and crosses NVLink (18 instead of 49 MB per step)
+        live = getattr(ops, "live_candidates", lambda k: cand_scores.shape[-1])(k_probe)
+        if live < cand_scores.shape[-1]:
+            part = cand_scores[..., :live].contiguous()
+            cand_scores[..., :live] = comm.all_reduce_max(part)
+        else:
+            cand_scores = comm.all_reduce_max(cand_scores)
     return ops.top(cand_ids, cand_scores, n_cand, len(seq_lens))
 
 
@@ -150,6 +157,10 @@ class GpuOps:
                                               self._p(plan.rowmap), self.n_rows_global,
                                               self.owned[0], self.owned[1], self._p(cid), self._p(csc), self._p(nc)))
         return cid, csc, nc
+
+    def live_candidates(self, k):
+        """Columns of the candidate tables that can hold a candidate: k results per query row x max_len rows."""
+        return min(SEQ_MAXC, -(-k * self.max_len // 64) * 64)
 
     def top(self, cand_ids, cand_scores, n_cand, n_len):
         n_test = cand_ids.shape[0]
