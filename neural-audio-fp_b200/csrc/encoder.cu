@@ -75,6 +75,7 @@ struct ConvParams {
     int n_streams;   // CTAs per combo; CTA c works on combo c % combos, unit c / combos, + n_streams, ...
     int n_units;     // units per combo: segments (ms >= 128) or 128-row groups of whole segments (ms < 128)
     int l2_prefetch; // 1 = the producer prefetches the next units' A boxes into L2
+    int tma_store;   // 1 = z leaves through a swizzled shared-memory tile and TMA stores (full-tile layers, fp16 output)
 };
 
 struct EncoderState {
@@ -99,8 +100,9 @@ struct EncoderState {
     cudaEvent_t ev_free[2] = {nullptr, nullptr};   // the last pass that read xin[b] has finished
     float* emb = nullptr;                      // (cap, 128)
     float* raw = nullptr;                      // (cap, 128) head outputs before the L2 normalisation
-    CUtensorMap tmA[ENC_LAYERS], tmB[ENC_LAYERS];
+    CUtensorMap tmA[ENC_LAYERS], tmB[ENC_LAYERS], tmO[ENC_LAYERS];     // activation in, weights, activation out (TMA store)
     bool weights = false;
+    int tma_store = 1;                         // NAFP_ENC_TMASTORE=0: direct 32-byte stores from the epilogue registers (A/B)
     int l2_prefetch = 0;                       // NAFP_ENC_L2PF=1 makes the producers prefetch the next unit's A boxes into L2
                                                // (measured: 7.5 vs 6.9 ms per 4,000 segments -- the UTMAPF requests compete
                                                // with the loads for the same TMA / L2 request slots; kept as a switch)
@@ -316,7 +318,8 @@ constexpr int CONV_EPI_PARTS = CONV_EPI_WARPS / 4;
 constexpr int CONV_THREADS = (2 + CONV_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2.. epilogue
 constexpr int CONV_A_BYTES = 128 * 128;    // 128 rows x 64 fp16
 constexpr int CONV_RING_BYTES = 192 * 1024;
-constexpr int CONV_SMEM = CONV_RING_BYTES + 256 + 1024;
+constexpr int CONV_STAGE_BYTES = 128 * 256;          // output staging: 128 rows x 128 fp16 channels, two SWIZZLE_128B halves
+constexpr int CONV_SMEM = CONV_RING_BYTES + CONV_STAGE_BYTES + 256 + 1024;
 constexpr int TMEM_GAMMA = 256, TMEM_CBETA = 384;          // NTILE = 128: column offsets of the parameter planes
 
 struct ConvBars {
@@ -369,7 +372,7 @@ template <int NTILE>
 // 18 warps: five share a sub-partition's 16 K registers -> at most 96 per thread (112 does not launch)
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvParams p, const float2* __restrict__ stat_in, const float* __restrict__ gamma,
+                 const __grid_constant__ CUtensorMap tmO, const ConvParams p, const float2* __restrict__ stat_in, const float* __restrict__ gamma,
                  const float* __restrict__ cbeta, const __half* __restrict__ cgam, __half* __restrict__ x_out,
                  float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
@@ -380,7 +383,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr bool STATIONARY = NTILE == 128;
     uint8_t* a_s = smem;                                        // [stage][128][128 B]
     uint8_t* b_s = smem + CONV_STAGES * CONV_A_BYTES;           // [stage][NTILE][128 B]  (or the resident weights)
-    ConvBars* bars = reinterpret_cast<ConvBars*>(smem + CONV_RING_BYTES);
+    uint8_t* o_s = smem + CONV_RING_BYTES;                      // [half 2][128 rows][128 B] output staging (tma_store)
+    ConvBars* bars = reinterpret_cast<ConvBars*>(o_s + CONV_STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_taps = p.tap_hi - p.tap_lo + 1;
@@ -396,6 +400,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.tma_store) tma_prefetch_desc(&tmO);
         for (int s = 0; s < CONV_STAGES; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
@@ -572,6 +577,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (un < p.n_units && bn < p.n_seg) st_next = __ldg(stat_in + bn);
             }
             __half* xrow = x_out + static_cast<int64_t>(m) * row_halves + n_base;
+            // TMA-store layers: the previous unit's tile must have left the staging buffer before it is rewritten
+            const bool use_tma = STATIONARY && CPW == 64 && p.tma_store;
+            if (use_tma) {
+                if (warp == 2 && lane == 0 && lt > 0) tma_store_wait_read();
+                asm volatile("bar.sync 1, %0;" ::"n"(CONV_EPI_WARPS * 32) : "memory");
+            }
             mbar_wait(&bars->tfull[acc], aph);
             tc_fence_after();
             uint64_t ps1 = pk2(0.f, 0.f), ps2 = pk2(0.f, 0.f);
@@ -609,7 +620,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t hi[8], lo[8];
                 // (loading chunk h + 1 while chunk h is computed was measured slower: 7.07 vs 6.26 ms per 4,000 segments)
                 conv_epi_chunk(va, vg, vb, STATIONARY ? &cg[(STATIONARY ? h : 0) * 8] : cgl, sta, stc, split, ps1, ps2, hi, lo);
-                if (row_ok) {
+                if (use_tma) {
+                    // row r of half `cpart`: 16-byte chunk c of the 128-byte row sits at chunk (c ^ (r & 7)) (SWIZZLE_128B);
+                    // 8 consecutive rows cover all 32 banks: a warp's store is conflict-free
+                    uint8_t* srow = o_s + cpart * (CONV_STAGE_BYTES / 2) + r * 128;
+                    *reinterpret_cast<uint4*>(srow + (((2 * h) ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(srow + (((2 * h + 1) ^ (r & 7)) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                } else if (row_ok) {
                     uint4* dst = reinterpret_cast<uint4*>(xrow + h * 16);
                     dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -621,6 +638,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         d2[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         d2[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
+                }
+            }
+            if (use_tma) {
+                // generic-proxy writes -> visible to the async proxy, all 8 warps done, then ONE thread stores the tile:
+                // two boxes of 64 channels x 128 rows = 32 KB contiguous in global memory (was 64 scattered 32-byte
+                // stores per warp: 32 L1 wavefronts per instruction)
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" ::"n"(CONV_EPI_WARPS * 32) : "memory");
+                if (warp == 2 && lane == 0) {
+                    const int m0 = u * p.ms + ptile * 128;
+                    tma_store_2d(&tmO, o_s, n0, m0);
+                    tma_store_2d(&tmO, o_s + CONV_STAGE_BYTES / 2, n0 + 64, m0);
+                    tma_store_commit();
                 }
             }
             // LayerNorm statistics of ELU(...): reduce over the rows of the same segment inside the warp, then one
@@ -652,6 +682,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
 
+    if (warp == 2 && lane == 0 && p.tma_store) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -759,6 +790,7 @@ static int encoder_init(nafp_ctx* ctx) {
     ctx->encoder = s;              // before the first fallible call: nafp_ctx_destroy releases it
     build_geometry(s->g);
     if (const char* e = getenv("NAFP_ENC_L2PF")) s->l2_prefetch = atoi(e) != 0;
+    if (const char* e = getenv("NAFP_ENC_TMASTORE")) s->tma_store = atoi(e) != 0;
     NAFP_CUDA(cudaMalloc(&s->w0, 3 * 128 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->bias0, 128 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->ln_b15, 1024 * sizeof(float)));
@@ -860,6 +892,12 @@ static int encoder_reserve(nafp_ctx* ctx, int64_t n) {
         }
         NAFP_TRY(make_tensor_map(&s->tmA[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, s->x[l - 1], dims, str, box, nullptr,
                                  CU_TENSOR_MAP_SWIZZLE_128B));
+        // output map for the TMA-store layers: rows = NHWC positions of all segments, box = 128 rows x 64 channels
+        const uint64_t od[2] = {static_cast<uint64_t>(L.c_out) * L.osplit, static_cast<uint64_t>(cap) * L.ms + 128};
+        const uint64_t os[2] = {2, static_cast<uint64_t>(L.c_out) * L.osplit * 2};
+        const uint32_t ob[2] = {64, 128};
+        NAFP_TRY(make_tensor_map(&s->tmO[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, s->x[l], od, os, ob, nullptr,
+                                 CU_TENSOR_MAP_SWIZZLE_128B));
     }
     s->cap = static_cast<int>(cap);
     return NAFP_OK;
@@ -911,10 +949,11 @@ static int encoder_pass(nafp_ctx* ctx, const float* mel, const int32_t* gmax, in
             if (p.n_streams > p.n_units) p.n_streams = p.n_units;
             if (p.n_streams < 1) p.n_streams = 1;
             p.l2_prefetch = s->l2_prefetch;
+            p.tma_store = (s->tma_store && L.nt == 128 && L.ms >= 128 && L.osplit == 1 && CONV_EPI_PARTS == 2) ? 1 : 0;
             slots = p.groups * p.n_ntiles * CONV_EPI_PARTS;
             auto kern = L.nt == 128 ? conv_gemm_kernel<128> : conv_gemm_kernel<256>;
             kern<<<p.combos * p.n_streams, CONV_THREADS, CONV_SMEM, st>>>(
-                s->tmA[l], s->tmB[l], p, s->stat + static_cast<size_t>(l - 1) * s->cap, s->ln_g[l], s->cbeta[l], s->cgam[l],
+                s->tmA[l], s->tmB[l], s->tmO[l], p, s->stat + static_cast<size_t>(l - 1) * s->cap, s->ln_g[l], s->cbeta[l], s->cgam[l],
                 s->x[l], s->part);
         }
         ln_stats_kernel<<<(n + 7) / 8, 256, 0, st>>>(s->part, slots, per, n, stat);
