@@ -215,6 +215,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     from oracle import native
+    native.lib().orc_set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: this arm owns the host
     threads = native.threads()
     n_full = args.db_rows + N_DB
     db = _cpu_rows(N_DB, 13)

@@ -35,7 +35,7 @@ typedef enum {
     NAFP_ERR_UNSUPPORTED = -4 /* valid in the reference but outside the hot path built here */
 } nafp_status;
 
-enum { NAFP_INDEX_FLAT_L2 = 0, NAFP_INDEX_IVFPQ = 1, NAFP_INDEX_IVF_FLAT = 2 };
+enum { NAFP_INDEX_FLAT_L2 = 0, NAFP_INDEX_IVFPQ = 1, NAFP_INDEX_IVF_FLAT = 2, NAFP_INDEX_IVFPQR = 3 };
 
 /* ------------------------------------------------------------------ library / context */
 int nafp_version(void);
@@ -139,8 +139,9 @@ int nafp_encoder_activation_host(nafp_ctx* ctx, int layer, int64_t n_seg, float*
 
 /* ------------------------------------------------------------------ index
  * Replaces the object returned by get_index() (eval/utils/get_index_faiss.py:10-121) for
- * index_type 'l2' (faiss.IndexFlatL2, :58), 'ivfpq' (faiss.IndexIVFPQ(flat,d,256,64,8), :69-74) and
- * 'ivf' (faiss.IndexIVFFlat(flat,d,400), :63-66; pq_m / pq_nbits are ignored for it).
+ * index_type 'l2' (faiss.IndexFlatL2, :58), 'ivfpq' (faiss.IndexIVFPQ(flat,d,256,64,8), :69-74),
+ * 'ivf' (faiss.IndexIVFFlat(flat,d,400), :63-66; pq_m / pq_nbits are ignored for it) and 'ivfpq-rr'
+ * (faiss.IndexIVFPQR, :75-85: the IVF-PQ search for 4 k candidates, re-ranked with a 4 x 4-bit refinement quantizer).
  */
 int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int pq_nbits,
                       nafp_index** out);
@@ -154,6 +155,10 @@ int nafp_index_add_dev(nafp_index* idx, const float* x_dev, int64_t n);
  * e.g. to reuse one training across shards; import is only allowed on an empty index. */
 int nafp_index_ivfpq_get_params(nafp_index* idx, float* coarse_host, float* pq_host);
 int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const float* pq_host);
+/* IVFPQR ('ivfpq-rr', faiss.IndexIVFPQR(flat, d, 256, 64, 8, M_refine 4, nbits_refine 4), get_index_faiss.py:75-85):
+ * the refinement codebooks ((4, 16, 32) float32) in addition to nafp_index_ivfpq_get/set_params. */
+int nafp_index_ivfpqr_get_refine(nafp_index* idx, float* refine_pq_host);
+int nafp_index_ivfpqr_set_refine(nafp_index* idx, const float* refine_pq_host);
 /* IVF-Flat and IVF-PQ: the coarse quantizer alone ((nlist,128) float32); import only on an empty index
  * (an IVF-Flat index counts as trained afterwards). */
 int nafp_index_ivf_get_coarse(nafp_index* idx, float* coarse_host);

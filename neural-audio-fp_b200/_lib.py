@@ -71,6 +71,8 @@ _SIGS = {
     "nafp_index_add_dev": (c_int, [c_void_p, c_void_p, c_int64]),
     "nafp_index_ivfpq_get_params": (c_int, [c_void_p, c_void_p, c_void_p]),
     "nafp_index_ivfpq_set_params": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "nafp_index_ivfpqr_get_refine": (c_int, [c_void_p, c_void_p]),
+    "nafp_index_ivfpqr_set_refine": (c_int, [c_void_p, c_void_p]),
     "nafp_index_ivf_get_coarse": (c_int, [c_void_p, c_void_p]),
     "nafp_index_ivf_set_coarse": (c_int, [c_void_p, c_void_p]),
     "nafp_index_reserve": (c_int, [c_void_p, c_int64]),

@@ -1146,8 +1146,8 @@ extern "C" {
 int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int pq_nbits, nafp_index** out) {
     NAFP_REQUIRE(ctx && out, NAFP_ERR_INVALID, "nafp_index_create: NULL argument");
     *out = nullptr;
-    NAFP_REQUIRE(type == NAFP_INDEX_FLAT_L2 || type == NAFP_INDEX_IVFPQ || type == NAFP_INDEX_IVF_FLAT, NAFP_ERR_UNSUPPORTED,
-                 "nafp_index_create: index type %d is not built (l2, ivfpq, ivf)", type);
+    NAFP_REQUIRE(type == NAFP_INDEX_FLAT_L2 || type == NAFP_INDEX_IVFPQ || type == NAFP_INDEX_IVF_FLAT || type == NAFP_INDEX_IVFPQR,
+                 NAFP_ERR_UNSUPPORTED, "nafp_index_create: index type %d is not built (l2, ivfpq, ivf, ivfpq-rr)", type);
     NAFP_REQUIRE(d == D128, NAFP_ERR_UNSUPPORTED, "nafp_index_create: d=%d; only d=128 (MODEL.EMB_SZ) is built", d);
     NAFP_CUDA(cudaSetDevice(ctx->device));
     nafp_index* idx = new nafp_index();
@@ -1161,7 +1161,8 @@ int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int p
         return NAFP_ERR_CUDA;
     }
     if (type != NAFP_INDEX_FLAT_L2) {
-        int s = type == NAFP_INDEX_IVFPQ ? ivfpq_create(idx, nlist, pq_m, pq_nbits) : ivfflat_create(idx, nlist);
+        int s = type == NAFP_INDEX_IVF_FLAT ? ivfflat_create(idx, nlist) : ivfpq_create(idx, nlist, pq_m, pq_nbits);
+        if (s == NAFP_OK && type == NAFP_INDEX_IVFPQR) s = ivfpqr_enable(idx);
         if (s != NAFP_OK) {
             if (idx->ivf) ivfpq_destroy(idx);
             cudaFree(idx->maxn2);

@@ -80,6 +80,7 @@ int index_reserve(nafp_index* idx, int64_t n_total);
 // ivfpq.cu
 int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits);
 int ivfflat_create(nafp_index* idx, int nlist);
+int ivfpqr_enable(nafp_index* idx);       // IVFPQR: adds the refinement quantizer to a freshly created IVF-PQ state
 void ivfpq_destroy(nafp_index* idx);
 int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed);
 int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n);

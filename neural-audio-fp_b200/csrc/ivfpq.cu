@@ -35,6 +35,7 @@ namespace nafp {
 constexpr int PQ_MAX_M = 64;
 constexpr int PQ_KSUB = 256;
 constexpr int IVF_MAX_NLIST = 1024;
+constexpr int REFINE_M = 4, REFINE_KSUB = 16, REFINE_DSUB = 32, REFINE_KFACTOR = 4;
 constexpr int IVF_SCAN_CAP = 512;         // candidate buffer per (query, list) CTA: two 512-key sorts per list instead of two 1024-key ones
 
 struct IvfPq {
@@ -52,6 +53,15 @@ struct IvfPq {
     int32_t* lids = nullptr;      // [n]
     int32_t* loff = nullptr;      // [nlist + 1]
     int64_t sorted_cap = 0;
+    // IVFPQR (index_type 'ivfpq-rr', get_index_faiss.py:75-85): second-level product quantizer of the first level's
+    // residual x - xhat, M_refine 4 sub-spaces of 32 dims x 16 centroids (4 bit) = 2 bytes per row; the search asks the
+    // IVF-PQ for k * k_factor (faiss default 4) candidates and re-ranks them by |q - (xhat + rhat)|^2
+    bool refine = false;
+    float* rpq = nullptr;         // [4][16][32]
+    uint8_t* rcodes = nullptr;    // [cap][2]: nibbles (sub 0 | sub 1 << 4), (sub 2 | sub 3 << 4)
+    float* refD = nullptr;        // [nq_cap][REFINE_K]
+    int64_t* refI = nullptr;
+    int64_t ref_nq = 0;
     // search scratch
     int32_t* probes = nullptr;    // [nq_cap][nprobe_cap]
     float* partD = nullptr;       // [nprobe][nq_cap][k]
@@ -598,7 +608,139 @@ __global__ void ivfpq_scatter_kernel(const float* __restrict__ Ds, const int64_t
     I[static_cast<int64_t>(rows[w]) * k + j] = Is[i];
 }
 
+// ------------------------------------------------------------------------------------------ IVFPQR
+// xhat of a row from its list and PQ code: lane owns dims 4 lane .. 4 lane + 3 (two dsub = 2 sub-spaces, or one of 4, ...)
+__device__ __forceinline__ float4 pq_reconstruct_lane(const float* __restrict__ coarse, const float* __restrict__ pq, int m,
+                                                      int dsub, int list, const uint8_t* __restrict__ code, int lane) {
+    float4 v = reinterpret_cast<const float4*>(coarse + static_cast<int64_t>(list) * D128)[lane];
+    float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int dim = 4 * lane + j, sub = dim / dsub;
+        vv[j] += pq[(static_cast<int64_t>(sub) * PQ_KSUB + code[sub]) * dsub + (dim - sub * dsub)];
+    }
+    return v;
+}
+// nearest of the 16 refinement codewords of sub-space (lane / 8) for the 32-dim residual slice spread over 8 lanes
+// (4 dims each); every lane of the group returns the code.  Ties go to the lower code.
+__device__ __forceinline__ int refine_encode_group(const float4 r, const float* __restrict__ rpq, int lane) {
+    const int sub = lane >> 3, part = lane & 7;
+    float best = FLT_MAX;
+    int bi = 0;
+    for (int c = 0; c < REFINE_KSUB; ++c) {
+        const float4 w = reinterpret_cast<const float4*>(rpq + (static_cast<int64_t>(sub) * REFINE_KSUB + c) * REFINE_DSUB)[part];
+        const float d0 = r.x - w.x, d1 = r.y - w.y, d2 = r.z - w.z, d3 = r.w - w.w;
+        float d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (d < best) { best = d; bi = c; }
+    }
+    return bi;
+}
+// second-level residual of rows whose first-level residual r1 = x - coarse[list] is given (training): for every PQ
+// sub-space the nearest codeword is subtracted.  One thread per (row, sub-space).
+__global__ void ivfpqr_residual2_kernel(const float* __restrict__ r1, int64_t n, const float* __restrict__ pq, int m, int dsub,
+                                        float* __restrict__ r2) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    const int64_t row = t / m;
+    const int sub = static_cast<int>(t - row * m);
+    const float* rr = r1 + row * D128 + sub * dsub;
+    float best = FLT_MAX;
+    int bi = 0;
+    for (int c = 0; c < PQ_KSUB; ++c) {
+        const float* w = pq + (static_cast<int64_t>(sub) * PQ_KSUB + c) * dsub;
+        float d = 0.f;
+        for (int j = 0; j < dsub; ++j) {
+            const float e = rr[j] - w[j];
+            d = fmaf(e, e, d);
+        }
+        if (d < best) { best = d; bi = c; }
+    }
+    const float* w = pq + (static_cast<int64_t>(sub) * PQ_KSUB + bi) * dsub;
+    for (int j = 0; j < dsub; ++j) r2[row * D128 + sub * dsub + j] = rr[j] - w[j];
+}
+// add: refinement code of rows [row0, row0 + n): r2 = x - xhat, 4 nibbles.  One warp per row.
+__global__ void __launch_bounds__(256)
+ivfpqr_encode_kernel(const float* __restrict__ x32, const int32_t* __restrict__ assign, const uint8_t* __restrict__ codes,
+                     int64_t row0, int64_t n, const float* __restrict__ coarse, const float* __restrict__ pq, int m, int dsub,
+                     const float* __restrict__ rpq, uint8_t* __restrict__ rcodes) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int64_t row = row0 + r;
+    const float4 xh = pq_reconstruct_lane(coarse, pq, m, dsub, assign[row], codes + row * m, lane);
+    const float4 xv = reinterpret_cast<const float4*>(x32 + row * D128)[lane];
+    const int code = refine_encode_group(make_float4(xv.x - xh.x, xv.y - xh.y, xv.z - xh.z, xv.w - xh.w), rpq, lane);
+    const int c0 = __shfl_sync(0xffffffffu, code, 0), c1 = __shfl_sync(0xffffffffu, code, 8);
+    const int c2 = __shfl_sync(0xffffffffu, code, 16), c3 = __shfl_sync(0xffffffffu, code, 24);
+    if (lane == 0) {
+        rcodes[row * 2] = static_cast<uint8_t>(c0 | (c1 << 4));
+        rcodes[row * 2 + 1] = static_cast<uint8_t>(c2 | (c3 << 4));
+    }
+}
+// search: block = query row; its kc first-level candidates are re-scored as |q - (xhat + rhat)|^2 (a warp per candidate),
+// sorted by (distance, label), the k best are returned (IndexIVFPQR::search_preassigned)
+__global__ void __launch_bounds__(128)
+ivfpqr_rerank_kernel(const float* __restrict__ q, const float* __restrict__ candD, const int64_t* __restrict__ candI, int kc, int k,
+                     const int32_t* __restrict__ assign, const uint8_t* __restrict__ codes, const uint8_t* __restrict__ rcodes,
+                     const float* __restrict__ coarse, const float* __restrict__ pq, int m, int dsub, const float* __restrict__ rpq,
+                     int64_t label_offset, float* __restrict__ D, int64_t* __restrict__ I) {
+    __shared__ float d_s[128];
+    __shared__ int64_t i_s[128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t qi = blockIdx.x;
+    const float4 qv = reinterpret_cast<const float4*>(q + qi * D128)[lane];
+    for (int e = threadIdx.x; e < 128; e += blockDim.x) { d_s[e] = INFINITY; i_s[e] = LLONG_MAX; }
+    __syncthreads();
+    for (int c = warp; c < kc; c += 4) {
+        const int64_t id = candI[qi * kc + c];
+        if (id < 0) continue;
+        const int64_t row = id - label_offset;
+        float4 xh = pq_reconstruct_lane(coarse, pq, m, dsub, assign[row], codes + row * m, lane);
+        const int sub = lane >> 3;
+        const int code = (rcodes[row * 2 + (sub >> 1)] >> (4 * (sub & 1))) & 15;
+        const float4 w = reinterpret_cast<const float4*>(rpq + (static_cast<int64_t>(sub) * REFINE_KSUB + code) * REFINE_DSUB)[lane & 7];
+        const float d0 = qv.x - (xh.x + w.x), d1 = qv.y - (xh.y + w.y), d2 = qv.z - (xh.z + w.z), d3 = qv.w - (xh.w + w.w);
+        float d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) { d_s[c] = d; i_s[c] = id; }
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= 128; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const int i = threadIdx.x, ixj = i ^ j;
+            if (ixj > i) {
+                const float da = d_s[i], db = d_s[ixj];
+                const int64_t ia = i_s[i], ib = i_s[ixj];
+                const bool a_after_b = (da > db) || (da == db && ia > ib);
+                const bool asc = (i & kk) == 0;
+                if (asc ? a_after_b : !a_after_b) {
+                    d_s[i] = db; d_s[ixj] = da;
+                    i_s[i] = ib; i_s[ixj] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const int64_t id = i_s[j];
+        D[qi * k + j] = id == LLONG_MAX ? INFINITY : d_s[j];
+        I[qi * k + j] = id == LLONG_MAX ? -1 : id;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
+int ivfpqr_enable(nafp_index* idx) {
+    IvfPq* s = idx->ivf;
+    NAFP_REQUIRE(s && !s->flat_lists && D128 == REFINE_M * REFINE_DSUB, NAFP_ERR_INVALID, "ivfpq-rr: needs an IVF-PQ state");
+    NAFP_CUDA(cudaMalloc(&s->rpq, static_cast<size_t>(REFINE_M) * REFINE_KSUB * REFINE_DSUB * sizeof(float)));
+    s->refine = true;
+    return NAFP_OK;
+}
+
 int ivfflat_create(nafp_index* idx, int nlist) {
     NAFP_REQUIRE(nlist >= 1 && nlist <= IVF_MAX_NLIST, NAFP_ERR_INVALID, "ivf: nlist=%d outside [1,%d]", nlist, IVF_MAX_NLIST);
     IvfPq* s = new IvfPq();
@@ -635,7 +777,8 @@ void ivfpq_destroy(nafp_index* idx) {
     if (!s) return;
     if (s->recon) nafp_index_destroy(s->recon);
     void* bufs[] = {s->coarse, s->pq, s->assign, s->codes, s->lcodes, s->lids, s->loff, s->probes, s->partD, s->partI,
-                    s->xhat_tmp, s->candD, s->candI, s->probes_all, s->redo_rows, s->redo_q, s->redo_D, s->redo_I};
+                    s->xhat_tmp, s->candD, s->candI, s->probes_all, s->redo_rows, s->redo_q, s->redo_D, s->redo_I,
+                    s->rpq, s->rcodes, s->refD, s->refI};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     idx->ivf = nullptr;
@@ -677,6 +820,16 @@ int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed) {
         NAFP_TRY(run_kmeans(ctx, r_dev + sub * s->dsub, nt, D128, s->dsub, PQ_KSUB,
                             s->pq + static_cast<size_t>(sub) * PQ_KSUB * s->dsub, a_dev, 25,
                             static_cast<uint64_t>(seed) + 2 + sub));
+    if (s->refine) {
+        // second level: residual of the first level on the training rows (r_dev -> x_dev), one k-means per 32-dim slice
+        ivfpqr_residual2_kernel<<<static_cast<unsigned>((nt * s->m + 255) / 256), 256, 0, ctx->stream>>>(r_dev, nt, s->pq, s->m,
+                                                                                                       s->dsub, x_dev);
+        ctx->launches++;
+        for (int sub = 0; sub < REFINE_M; ++sub)
+            NAFP_TRY(run_kmeans(ctx, x_dev + sub * REFINE_DSUB, nt, D128, REFINE_DSUB, REFINE_KSUB,
+                                s->rpq + static_cast<size_t>(sub) * REFINE_KSUB * REFINE_DSUB, a_dev, 25,
+                                static_cast<uint64_t>(seed) + 100 + sub));
+    }
     NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     s->trained = true;
     return NAFP_OK;
@@ -697,6 +850,16 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
                 NAFP_CUDA(cudaMemcpyAsync(c, s->codes, static_cast<size_t>(row0) * s->m, cudaMemcpyDeviceToDevice, ctx->stream));
             NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
         }
+        if (s->refine) {
+            uint8_t* rc = nullptr;
+            NAFP_CUDA(cudaMalloc(&rc, static_cast<size_t>(idx->cap) * 2));
+            if (row0 > 0) {
+                NAFP_CUDA(cudaMemcpyAsync(rc, s->rcodes, static_cast<size_t>(row0) * 2, cudaMemcpyDeviceToDevice, ctx->stream));
+                NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
+            }
+            if (s->rcodes) cudaFree(s->rcodes);
+            s->rcodes = rc;
+        }
         if (s->assign) cudaFree(s->assign);
         if (s->codes) cudaFree(s->codes);
         s->assign = a;
@@ -716,6 +879,11 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
     ivfpq_encode_kernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(idx->x32, row0, n, s->coarse, s->nlist, s->pq,
                                                                               s->m, s->dsub, s->assign, s->codes);
     ctx->launches++;
+    if (s->refine) {
+        ivfpqr_encode_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            idx->x32, s->assign, s->codes, row0, n, s->coarse, s->pq, s->m, s->dsub, s->rpq, s->rcodes);
+        ctx->launches++;
+    }
     NAFP_CUDA(cudaGetLastError());
     s->dirty = true;
     NAFP_TRY(index_reserve(s->recon, idx->cap));
@@ -788,8 +956,8 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
     nafp_ctx* ctx = idx->ctx;
     if (nq == 0) return NAFP_OK;
     const int nprobe = idx->nprobe < s->nlist ? idx->nprobe : s->nlist;
-    NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
-                 "ivfpq search: need k <= %d and nprobe*k <= 2048 (nprobe %d, k %d)", MAX_K, nprobe, k);
+    NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 4096, NAFP_ERR_INVALID,
+                 "ivfpq search: need k <= %d and nprobe*k <= 4096 (nprobe %d, k %d)", MAX_K, nprobe, k);
     NAFP_TRY(build_lists(idx));
     const int64_t n_search = (idx->search_rows >= 0 && idx->search_rows < idx->n) ? idx->search_rows : idx->n;
     const int64_t chunk = 4096;       // query rows per launch group (bounds the partial buffers)
@@ -829,15 +997,44 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
     return NAFP_OK;
 }
 
+static int ivfpq_search_first_level(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev);
+
 int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+    IvfPq* s = idx->ivf;
+    if (!s->refine) return ivfpq_search_first_level(idx, q_dev, nq, k, D_dev, I_dev);
+    // IVFPQR: k * k_factor first-level candidates (faiss default k_factor 4), re-ranked with the refinement codes
+    nafp_ctx* ctx = idx->ctx;
+    NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "ivfpq-rr search: index is not trained");
+    const int kc = k * REFINE_KFACTOR;
+    NAFP_REQUIRE(k >= 1 && kc <= MAX_K, NAFP_ERR_INVALID, "ivfpq-rr search: k=%d (k * %d candidates must be <= %d)", k, REFINE_KFACTOR, MAX_K);
+    NAFP_CUDA(cudaSetDevice(ctx->device));
+    if (nq == 0) return NAFP_OK;
+    if (s->ref_nq < nq) {
+        if (s->refD) cudaFree(s->refD);
+        if (s->refI) cudaFree(s->refI);
+        s->refD = nullptr; s->refI = nullptr; s->ref_nq = 0;
+        NAFP_CUDA(cudaMalloc(&s->refD, static_cast<size_t>(nq) * MAX_K * sizeof(float)));
+        NAFP_CUDA(cudaMalloc(&s->refI, static_cast<size_t>(nq) * MAX_K * sizeof(int64_t)));
+        s->ref_nq = nq;
+    }
+    NAFP_TRY(ivfpq_search_first_level(idx, q_dev, nq, kc, s->refD, s->refI));
+    ivfpqr_rerank_kernel<<<static_cast<unsigned>(nq), 128, 0, ctx->stream>>>(q_dev, s->refD, s->refI, kc, k, s->assign, s->codes, s->rcodes,
+                                                                             s->coarse, s->pq, s->m, s->dsub, s->rpq,
+                                                                             idx->label_offset, D_dev, I_dev);
+    ctx->launches++;
+    NAFP_CUDA(cudaGetLastError());
+    return NAFP_OK;
+}
+
+static int ivfpq_search_first_level(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
     IvfPq* s = idx->ivf;
     nafp_ctx* ctx = idx->ctx;
     NAFP_REQUIRE(s->trained, NAFP_ERR_STATE, "ivfpq search: index is not trained");
     NAFP_CUDA(cudaSetDevice(ctx->device));
     if (nq == 0) return NAFP_OK;
     const int nprobe = idx->nprobe < s->nlist ? idx->nprobe : s->nlist;
-    NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 2048, NAFP_ERR_INVALID,
-                 "ivfpq search: need k <= %d and nprobe*k <= 2048 (nprobe %d, k %d)", MAX_K, nprobe, k);
+    NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 4096, NAFP_ERR_INVALID,
+                 "ivfpq search: need k <= %d and nprobe*k <= 4096 (nprobe %d, k %d)", MAX_K, nprobe, k);
     if (!s->flat_lists) idx->host_rows += nq;          // (the flat scan of an IVF-Flat index counts its own rows)
     if (k > RECON_K / 2 || nq >= (1ll << 31)) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
 
@@ -957,6 +1154,25 @@ int nafp_index_ivfpq_set_params(nafp_index* idx, const float* coarse_host, const
     NAFP_CUDA(cudaMemcpy(s->coarse, coarse_host, static_cast<size_t>(s->nlist) * D128 * sizeof(float), cudaMemcpyHostToDevice));
     NAFP_CUDA(cudaMemcpy(s->pq, pq_host, static_cast<size_t>(s->m) * PQ_KSUB * s->dsub * sizeof(float), cudaMemcpyHostToDevice));
     s->trained = true;
+    return NAFP_OK;
+}
+
+int nafp_index_ivfpqr_get_refine(nafp_index* idx, float* refine_pq_host) {
+    NAFP_RANGE("nafp_index_ivfpqr_get_refine");
+    NAFP_REQUIRE(idx && idx->ivf && idx->ivf->refine && refine_pq_host, NAFP_ERR_INVALID, "nafp_index_ivfpqr_get_refine: not an IVFPQR index");
+    NAFP_REQUIRE(idx->ivf->trained, NAFP_ERR_STATE, "nafp_index_ivfpqr_get_refine: index is not trained");
+    NAFP_CUDA(cudaStreamSynchronize(idx->ctx->stream));
+    NAFP_CUDA(cudaMemcpy(refine_pq_host, idx->ivf->rpq, static_cast<size_t>(REFINE_M) * REFINE_KSUB * REFINE_DSUB * sizeof(float),
+                         cudaMemcpyDeviceToHost));
+    return NAFP_OK;
+}
+
+int nafp_index_ivfpqr_set_refine(nafp_index* idx, const float* refine_pq_host) {
+    NAFP_RANGE("nafp_index_ivfpqr_set_refine");
+    NAFP_REQUIRE(idx && idx->ivf && idx->ivf->refine && refine_pq_host, NAFP_ERR_INVALID, "nafp_index_ivfpqr_set_refine: not an IVFPQR index");
+    NAFP_REQUIRE(idx->n == 0, NAFP_ERR_STATE, "nafp_index_ivfpqr_set_refine: index already holds rows");
+    NAFP_CUDA(cudaMemcpy(idx->ivf->rpq, refine_pq_host, static_cast<size_t>(REFINE_M) * REFINE_KSUB * REFINE_DSUB * sizeof(float),
+                         cudaMemcpyHostToDevice));
     return NAFP_OK;
 }
 

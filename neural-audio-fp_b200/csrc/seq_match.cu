@@ -267,8 +267,8 @@ seq_top_kernel(int n_len, const int64_t* __restrict__ cand_ids, const float* __r
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const float* __restrict__ D_all, const int64_t* __restrict__ I_all, int W, int64_t nq, int k,
                   float* __restrict__ D_out, int64_t* __restrict__ I_out) {
-    __shared__ float d_s[2048];
-    __shared__ int64_t i_s[2048];
+    __shared__ float d_s[4096];          // 16 + 32 KB: the static shared-memory limit
+    __shared__ int64_t i_s[4096];
     const int64_t q = blockIdx.x;
     const int n = W * k;
     int npow = 1;
@@ -397,7 +397,7 @@ int nafp_topk_merge_dev(nafp_ctx* ctx, const float* D_all_dev, const int64_t* I_
                         int64_t nq, int32_t k, float* D_out_dev, int64_t* I_out_dev) {
     NAFP_RANGE("nafp_topk_merge_dev");
     NAFP_REQUIRE(ctx && D_all_dev && I_all_dev && D_out_dev && I_out_dev && n_shards >= 1 && k >= 1 &&
-                     n_shards * k <= 2048, NAFP_ERR_INVALID, "nafp_topk_merge_dev: need n_shards*k <= 2048");
+                     n_shards * k <= 4096, NAFP_ERR_INVALID, "nafp_topk_merge_dev: need n_shards*k <= 4096");
     if (nq == 0) return NAFP_OK;
     topk_merge_kernel<<<static_cast<unsigned>(nq), 128, 0, ctx->stream>>>(D_all_dev, I_all_dev, n_shards, nq, k,
                                                                           D_out_dev, I_out_dev);

@@ -70,7 +70,7 @@ def _sharded_index(index_type, dummy_db, db, max_len, max_train, rank, world, de
     kinds = {'l2': FLAT_L2, 'ivfpq': IVFPQ, 'ivf': IVF_FLAT}
     mode = index_type.lower()
     if mode not in kinds:
-        raise NotImplementedError(f"index_type '{mode}' is not built (l2, ivfpq, ivf)")
+        raise NotImplementedError(f"index_type '{mode}' is not available row-sharded (l2, ivfpq, ivf are)")
     comm = None
     if world > 1:
         import torch
@@ -95,9 +95,25 @@ def _sharded_index(index_type, dummy_db, db, max_len, max_train, rank, world, de
     return index
 
 
+def _check_limits(index_type, test_seq_len, k_probe, nprobe=40):
+    """The kernels' table sizes, checked before any data is loaded (the reference has no such limits; all of its
+    defaults -- lengths <= 19, k_probe 20, nprobe 40 -- are inside them)."""
+    if len(test_seq_len) == 0 or min(test_seq_len) < 1 or max(test_seq_len) > 32:
+        raise ValueError(f"--test_seq_len {list(test_seq_len)}: sequence lengths must be in 1..32 (matcher kernels)")
+    if k_probe < 1 or k_probe > 128 or k_probe * int(max(test_seq_len)) > 1024:
+        raise ValueError(f"--k_probe {k_probe}: need 1 <= k_probe <= 128 and k_probe x max(test_seq_len) <= 1024 "
+                         f"(candidate table of the matcher), got {k_probe * int(max(test_seq_len))}")
+    mode = index_type.lower()
+    if mode in ('ivfpq', 'ivf') and nprobe * k_probe > 4096:
+        raise ValueError(f"--k_probe {k_probe}: index_type {mode} needs nprobe x k_probe <= 4096 (nprobe {nprobe})")
+    if mode == 'ivfpq-rr' and 4 * k_probe > 128:
+        raise ValueError(f"--k_probe {k_probe}: index_type ivfpq-rr re-ranks 4 x k_probe candidates, at most 128")
+
+
 def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_train=1e7, test_ids='icassp',
              test_seq_len='1 3 5 9 11 19', k_probe=20, display_interval=5, device=0, live=None, sharded=None):
     test_seq_len = np.asarray(list(map(int, test_seq_len.split())))
+    _check_limits(index_type, test_seq_len, int(k_probe))
     world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
     if sharded is None:
         sharded = world > 1
@@ -154,7 +170,11 @@ def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_t
         start_time = time.time()
         ids = test_ids[b0:b0 + block]
         assert (ids <= len(query)).all()
-        pred, _ = index.seq_match(query_np, ids, test_seq_len, k_probe)
+        # only the query rows this block can touch cross PCIe (ids of a block are close together for sorted id
+        # lists such as the ICASSP one: ~1/8 of the query set per block instead of all of it every time)
+        q_lo = int(ids.min())
+        q_hi = min(int(ids.max()) + int(max(test_seq_len)), len(query_np))
+        pred, _ = index.seq_match(query_np[q_lo:q_hi], ids - q_lo, test_seq_len, k_probe)
         for j in range(len(ids)):
             ti = b0 + j
             for si in range(n_len):
@@ -183,7 +203,7 @@ def run_eval(emb_dir, emb_dummy_dir=None, index_type='ivfpq', nogpu=False, max_t
 @click.option('--emb_dummy_dir', default=None, type=click.STRING,
               help="Specify a directory containing 'dummy_db.mm' and 'dummy_db_shape.npy' to use. Default is EMB_DIR.")
 @click.option('--index_type', '-i', default='ivfpq', type=click.STRING,
-              help="Index type must be one of {'L2', 'IVF', 'IVFPQ'} ('IVFPQ-RR', 'IVFPQ-ONDISK', 'HNSW' are not built).")
+              help="Index type must be one of {'L2', 'IVF', 'IVFPQ', 'IVFPQ-RR'} ('IVFPQ-ONDISK' and 'HNSW' are CPU-only in the reference).")
 @click.option('--nogpu', default=False, is_flag=True, help='Refused: this build has no CPU search path.')
 @click.option('--max_train', default=1e7, type=click.INT, help='Max number of items for index training. Default is 1e7.')
 @click.option('--test_seq_len', default='1 3 5 9 11 19', type=click.STRING,

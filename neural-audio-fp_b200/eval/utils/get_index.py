@@ -4,9 +4,9 @@ libnafp instead of faiss.
 ``get_index(index_type, train_data, train_data_shape, use_gpu, max_nitem_train)`` returns an object
 with the faiss surface the reference uses: ``train(x)``, ``add(x)``, ``ntotal``, ``nprobe``
 (attribute), ``search(q, k) -> (D, I)`` (squared-L2 ascending, int64 labels, -1 padding),
-``reconstruct_n(i0, n)``.  Built: 'l2', 'ivfpq' (the hot path) and 'ivf' (IndexIVFFlat, nlist 400).
-'ivfpq-rr', 'ivfpq-ondisk' and 'hnsw' raise NotImplementedError, like the reference does for the modes
-it cannot serve.
+``reconstruct_n(i0, n)``.  Built: 'l2', 'ivfpq' (the hot path), 'ivf' (IndexIVFFlat, nlist 400) and 'ivfpq-rr'
+(IndexIVFPQR).  'ivfpq-ondisk' and 'hnsw' raise NotImplementedError("... only available in CPU"), which is what the
+reference does for them whenever use_gpu is set (``get_index_faiss.py:86-98``).
 """
 from __future__ import annotations
 
@@ -17,7 +17,7 @@ import numpy as np
 
 from ..._lib import Context, NafpError, check, lib, ptr
 
-FLAT_L2, IVFPQ, IVF_FLAT = 0, 1, 2
+FLAT_L2, IVFPQ, IVF_FLAT, IVFPQR = 0, 1, 2, 3
 _ADD_CHUNK = 1 << 20      # rows per host->device copy (memmaps are read chunk by chunk)
 
 
@@ -73,6 +73,18 @@ class Index:
         pq = np.empty((self.pq_m, 256, 128 // self.pq_m), np.float32)
         check(lib.nafp_index_ivfpq_get_params(self.h, ptr(coarse), ptr(pq)))
         return coarse, pq
+
+    def ivfpqr_refine(self):
+        """(4, 16, 32) refinement codebooks of a trained IVFPQR index."""
+        rpq = np.empty((4, 16, 32), np.float32)
+        check(lib.nafp_index_ivfpqr_get_refine(self.h, ptr(rpq)))
+        return rpq
+
+    def set_ivfpqr_refine(self, rpq):
+        rpq = _f32c(rpq)
+        if rpq.shape != (4, 16, 32):
+            raise ValueError("expected (4, 16, 32) refinement codebooks")
+        check(lib.nafp_index_ivfpqr_set_refine(self.h, ptr(rpq)))
 
     def ivf_coarse(self):
         """(nlist,128) coarse centroids of a trained IVF-Flat / IVF-PQ index."""
@@ -175,8 +187,12 @@ def get_index(index_type, train_data, train_data_shape, use_gpu=True, max_nitem_
     elif mode == 'ivf':
         # reference: IndexIVFFlat, nlist 400 (get_index_faiss.py:63-66)
         index = Index(IVF_FLAT, d, nlist=400, device=device)
-    elif mode in ('ivfpq-rr', 'ivfpq-ondisk', 'hnsw'):
-        raise NotImplementedError(f"index_type '{mode}' is not built (l2, ivfpq, ivf)")
+    elif mode == 'ivfpq-rr':
+        # reference: IndexIVFPQR, code_sz 64, n_centroids 256, nbits 8, M_refine 4, nbits_refine 4 (get_index_faiss.py:75-85)
+        index = Index(IVFPQR, d, nlist=256, pq_m=64, pq_nbits=8, device=device)
+    elif mode in ('ivfpq-ondisk', 'hnsw'):
+        # get_index_faiss.py:86-98: both raise under use_gpu, and this build has no CPU path
+        raise NotImplementedError(f'{mode} is only available in CPU.')
     else:
         raise ValueError(mode)
 

@@ -201,3 +201,67 @@ class IVFPQ:
             D[i, :len(order)] = ds[order]
             I[i, :len(order)] = ids[order]
         return D, I
+
+
+class IVFPQR(IVFPQ):
+    """Oracle of ``faiss.IndexIVFPQR(flat, d, 256, 64, 8, M_refine=4, nbits_refine=4)`` (``get_index_faiss.py:75-85``),
+    restated from faiss' published algorithm: a second product quantizer (4 sub-spaces of d/4 dims, 16 centroids each:
+    2 bytes per row) is trained on and encodes the residual x - xhat of the IVF-PQ reconstruction; ``search`` takes
+    ``k * k_factor`` (default 4) candidates from the IVF-PQ search and re-ranks them by |q - (xhat + rhat)|^2.
+    PARITY UNPINNED against faiss (same caveats as ``IVFPQ``)."""
+
+    M_REFINE, KSUB_REFINE, K_FACTOR = 4, 16, 4
+
+    def __init__(self, d=128, nlist=256, m=64, nbits=8):
+        super().__init__(d, nlist, m, nbits)
+        self.rdsub = d // self.M_REFINE
+        self.rpq = None                                   # (4, 16, d/4)
+        self.rcodes = np.zeros((0, self.M_REFINE), np.uint8)
+
+    def set_refine(self, rpq):
+        self.rpq = np.ascontiguousarray(rpq, np.float32).reshape(self.M_REFINE, self.KSUB_REFINE, self.rdsub)
+
+    def _first_level(self, x):
+        """(list, PQ code, xhat) of rows x -- the IVF-PQ encoding ``add`` performs."""
+        a = self._assign(x)
+        r = (x - self.coarse[a]).reshape(len(x), self.m, self.dsub)
+        d = ((r[:, :, None, :] - self.pq[None]) ** 2).sum(-1)
+        c = d.argmin(2).astype(np.uint8)
+        xhat = self.coarse[a] + self.pq[np.arange(self.m)[None, :], c].reshape(len(x), self.d)
+        return a, c, xhat
+
+    def train(self, x, seed=1234):
+        x = np.ascontiguousarray(x, np.float32)
+        super().train(x, seed=seed)
+        xt = x[select_rows(len(x), 256 * max(self.nlist, self.ksub), seed)]
+        _, _, xhat = self._first_level(xt)
+        r2 = np.ascontiguousarray((xt - xhat).reshape(len(xt), self.M_REFINE, self.rdsub).transpose(1, 0, 2))
+        self.rpq, _ = kmeans_batched(r2, self.KSUB_REFINE, [seed + 100 + j for j in range(self.M_REFINE)])
+
+    def add(self, x, chunk=8192):
+        x = np.ascontiguousarray(x, np.float32)
+        rc = [self.rcodes]
+        for s0 in range(0, len(x), chunk):
+            xb = x[s0:s0 + chunk]
+            _, _, xhat = self._first_level(xb)
+            r2 = (xb - xhat).reshape(len(xb), self.M_REFINE, 1, self.rdsub)
+            rc.append(((r2 - self.rpq[None]) ** 2).sum(-1).argmin(2).astype(np.uint8))
+        super().add(x)
+        self.rcodes = np.concatenate(rc)
+
+    def search(self, q, k):
+        q = np.ascontiguousarray(q, np.float32)
+        _, I1 = super().search(q, k * self.K_FACTOR)
+        D = np.full((len(q), k), np.inf, np.float32)
+        I = np.full((len(q), k), -1, np.int64)
+        for i in range(len(q)):
+            ids = I1[i][I1[i] >= 0]
+            if len(ids) == 0:
+                continue
+            rec = self.reconstruct(ids) + self.rpq[np.arange(self.M_REFINE)[None, :], self.rcodes[ids]].reshape(len(ids), self.d)
+            d = ((q[i][None] - rec) ** 2).sum(1, dtype=np.float32)
+            order = np.lexsort((ids, d))[:k]
+            D[i, :len(order)] = d[order]
+            I[i, :len(order)] = ids[order]
+        return D, I
+

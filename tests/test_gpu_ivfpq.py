@@ -197,3 +197,59 @@ def test_ivf_flat_untrained_add_is_refused():
     g = Index(IVF_FLAT, 128, nlist=400)
     with pytest.raises(NafpError):
         g.add(np.zeros((4, 128), np.float32))
+
+
+def test_ivfpq_rr_same_quantizers_matches_oracle():
+    """index_type 'ivfpq-rr' (faiss.IndexIVFPQR, get_index_faiss.py:75-85): with the GPU-trained quantizers of both levels
+    handed to the oracle, codes, refinement codes and re-ranked answers agree; own training on both sides (same seed)
+    gives the same top-1 recall."""
+    from nafp_b200 import synth
+    from nafp_b200.eval.utils.get_index import IVFPQR, Index, get_index
+    from oracle.flat_index import FlatL2
+    from oracle.ivfpq_index import IVFPQR as OracleIVFPQR
+    dummy, db, query = synth.synth_search_set(20000, 590, seed=41)
+    g = Index(IVFPQR, 128, nlist=64, pq_m=64, pq_nbits=8)
+    g.train(dummy[:16000], seed=77)
+    g.add(dummy)
+    g.add(db)
+    g.nprobe = 16
+    o = OracleIVFPQR(128, 64, 64, 8)
+    o.set_params(*g.ivfpq_params())
+    o.set_refine(g.ivfpqr_refine())
+    o.add(dummy)
+    o.add(db)
+    o.nprobe = 16
+    q = query[:64]
+    Dg, Ig = g.search(q, 20)
+    Do, Io = o.search(q, 20)
+    assert ((Ig < 0) == (Io < 0)).all()
+    fin = np.isfinite(Do)
+    np.testing.assert_allclose(Dg[fin], Do[fin], rtol=0, atol=3e-5)
+    same = Ig == Io
+    assert same.mean() >= 0.97, same.mean()
+    for r, c in np.argwhere(~same):            # only permutations among near-equal refined distances / first-level ties at rank 80
+        assert abs(Dg[r, c] - Do[r, c]) < 3e-5 or Ig[r, c] in Io[r]
+    # the sequence matcher runs on it like on the other index types
+    ids = np.arange(0, 560, 20)
+    pred, _ = g.seq_match(query, ids, [1, 3, 5], 20)
+    assert (pred[:, 2, 0] == ids + len(dummy)).mean() > 0.9
+    # own training: oracle vs GPU
+    o2 = OracleIVFPQR(128, 64, 64, 8)
+    o2.train(dummy[:16000], seed=77)
+    o2.add(dummy)
+    o2.add(db)
+    o2.nprobe = 16
+    flat = FlatL2(128)
+    flat.add(dummy)
+    flat.add(db)
+    _, Ie = flat.search(query[:300], 1)
+    _, Ig2 = g.search(query[:300], 20)
+    _, Io2 = o2.search(query[:300], 20)
+    rg, ro = (Ig2[:, 0] == Ie[:, 0]).mean(), (Io2[:, 0] == Ie[:, 0]).mean()
+    assert abs(rg - ro) <= 0.02 and rg > 0.6, (rg, ro)
+    # factory + the reference's error for the CPU-only types
+    idx = get_index('ivfpq-rr', dummy[:8000], (8000, 128), True, 1e7)
+    assert idx.is_trained and idx.nprobe == 40
+    for mode in ('hnsw', 'ivfpq-ondisk'):
+        with pytest.raises(NotImplementedError, match='only available in CPU'):
+            get_index(mode, dummy[:100], (100, 128), True, 1e7)

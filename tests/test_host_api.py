@@ -134,3 +134,14 @@ def test_generate_reads_the_launcher_environment(monkeypatch):
     G._barrier_fn(1)()                                  # single rank: no process group is touched
     with pytest.raises(ValueError):
         G.generate_fingerprint({}, 'random-init', None, None, None, True, rank=2, world_size=2)
+
+
+def test_cli_limits_are_checked_up_front():
+    """limits of the matcher / IVF kernels surface as a clear ValueError before any data is touched."""
+    from nafp_b200.eval.eval_search import _check_limits
+    _check_limits('l2', [1, 3, 5, 9, 11, 19], 20)
+    _check_limits('ivfpq', [1, 19], 51)
+    _check_limits('ivfpq-rr', [1, 19], 20)
+    for args in (('l2', [1, 33], 20), ('l2', [19], 60), ('ivfpq', [1], 110), ('ivfpq-rr', [1], 40), ('l2', [], 20)):
+        with pytest.raises(ValueError):
+            _check_limits(*args)

@@ -73,3 +73,33 @@ def test_ivf_flat_all_lists_equals_exact_search_and_fewer_probes_lose_recall():
     small.nprobe = 20
     Ds, Is = small.search(query[:2], 20)
     assert (Is[:, 5:] == -1).all() and np.isinf(Ds[:, 5:]).all() and set(Is[0, :5]) == set(range(5))
+
+
+def test_ivfpqr_refinement_improves_the_ranking():
+    """IndexIVFPQR oracle: the 2-byte refinement codes shrink the reconstruction error and never hurt top-1 recall."""
+    from oracle.ivfpq_index import IVFPQR
+    dummy, db, query = synth.synth_search_set(6000, 590, seed=14)
+    rr = IVFPQR(128, nlist=16, m=64)
+    rr.train(dummy, seed=3)
+    assert rr.rpq.shape == (4, 16, 32)
+    rr.add(dummy)
+    rr.add(db)
+    rr.nprobe = 16
+    assert rr.rcodes.shape == (6590, 4) and rr.rcodes.max() < 16
+    x = np.concatenate([dummy, db])
+    rows = np.arange(0, 6590, 13)
+    e1 = np.linalg.norm(x[rows] - rr.reconstruct(rows), axis=1)
+    rec2 = rr.reconstruct(rows) + rr.rpq[np.arange(4)[None, :], rr.rcodes[rows]].reshape(len(rows), 128)
+    e2 = np.linalg.norm(x[rows] - rec2, axis=1)
+    assert e2.mean() < e1.mean()
+    flat = FlatL2(128)
+    flat.add(dummy)
+    flat.add(db)
+    _, Ie = flat.search(query[:60], 1)
+    D, I = rr.search(query[:60], 20)
+    D0, I0 = IVFPQ.search(rr, query[:60], 20)
+    assert (np.diff(D, axis=1) >= 0).all() and (I >= 0).all()
+    assert (I[:, 0] == Ie[:, 0]).mean() >= (I0[:, 0] == Ie[:, 0]).mean() - 0.02
+    # the refined list is a re-ordering of (a subset of) the 4k first-level candidates
+    _, I4 = IVFPQ.search(rr, query[:60], 80)
+    assert all(set(I[r]) <= set(I4[r]) for r in range(60))
