@@ -25,7 +25,7 @@
 //                      layers with K <= 384 keep their weights resident in shared memory.
 //   fold_kernel        (weights load) Cg / Cb of every layer in fp64
 //   divenc_kernel      last LayerNorm + divide-and-encode head (128 x [8->32 ELU, 32->1]); l2norm_kernel.
-// fp16 operands / fp32 accumulation; the ten small layers from L4a on run split precision (hi + lo operands).
+// fp16 operands / fp32 accumulation; the six small layers from L6a on run split precision (hi + lo operands).
 // Measured against the fp64 oracle the fingerprints agree to a few 1e-4 (gate: cosine >= 0.9999, max abs <= 1e-3).
 #include <cuda_fp16.h>
 
@@ -64,7 +64,11 @@ struct ConvGeom {
                                        // the same implicit GEMM then computes hi.hi + hi.lo + lo.hi
     int osplit;                        // split factor of this layer's stored output (= ksplit of its consumer)
 };
-constexpr int ENC_SPLIT_FROM = 6;      // layers >= L4a: 25 % of the flops; removes ~35 % of the fingerprint's worst-case fp16 error
+constexpr int ENC_SPLIT_FROM = 10;     // layers >= L6a run split precision.  Measured on B200 (120 segments x 3 weight sets, fp64 oracle;
+                                       // seg/s of a 4,000-segment pass): from L4a (round 1's choice) 636 k, rms 8.0e-5, max 3.9e-4;
+                                       // from L6a 760 k, rms 1.0e-4, max 4.9e-4; no split 821 k, rms 1.3e-4, max 6.1e-4 (gate 1e-3).
+                                       // One fp16 rounding per layer instead of round 1's two (LayerNorm folding) is what made
+                                       // room: round 1 measured 1.0e-3 without the split.
 
 struct ConvParams {
     int m_total, ms, n_seg, c_in, c_out, n_ntiles;
@@ -156,7 +160,9 @@ static void build_geometry(ConvGeom* g) {
     if (const char* e = getenv("NAFP_ENC_NT256")) nt256 = static_cast<unsigned>(strtoul(e, nullptr, 0));
     for (int l = 1; l < 16; ++l)
         if (((nt256 >> l) & 1u) && g[l].c_out >= 256 && g[l].ms < 128) g[l].nt = 256;
-    for (int l = 0; l < 16; ++l) g[l].ksplit = l >= ENC_SPLIT_FROM ? 3 : 1;
+    int split_from = ENC_SPLIT_FROM;           // NAFP_ENC_SPLIT_FROM: A/B of the error / speed trade (16 = no split layer)
+    if (const char* e = getenv("NAFP_ENC_SPLIT_FROM")) split_from = atoi(e);
+    for (int l = 0; l < 16; ++l) g[l].ksplit = l >= split_from ? 3 : 1;
     for (int l = 0; l < 16; ++l) g[l].osplit = l + 1 < 16 ? g[l + 1].ksplit : 3;     // the head reads hi + lo too
 }
 

@@ -823,6 +823,8 @@ flat_brute_scan_kernel(int k, int64_t n_rows, const float* __restrict__ q_all, c
             }
             __syncwarp();
             kth = lst[k - 1];
+            __syncwarp();            // every lane has read the list before lane 0 inserts again (racecheck: WAR warning;
+                                     // the shuffles of the next dot product ordered it in practice)
         }
     }
     __syncthreads();
