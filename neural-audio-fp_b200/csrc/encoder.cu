@@ -1109,8 +1109,20 @@ static int fingerprint_host(nafp_ctx* ctx, const void* x_host, bool pcm16, int64
     NAFP_TRY(encoder_reserve(ctx, n_seg < chunk ? n_seg : chunk));      // before s->xin / s->emb are read below
     const size_t elt = pcm16 ? sizeof(int16_t) : sizeof(float);
     const uint8_t* src = static_cast<const uint8_t*>(x_host);
-    auto upload = [&](int64_t s0, int b) -> cudaError_t {      // pass starting at s0 -> xin[b], on the copy stream
-        const int64_t n = n_seg - s0 < chunk ? n_seg - s0 : chunk;
+    // Pieces of whole groups: a short first piece (its upload is the only one no kernel hides: 16 MB instead of 64 MB
+    // of int16 PCM), then full encoder passes; the upload of piece i + 1 runs on the copy stream under the kernels of
+    // piece i.
+    std::vector<int64_t> piece_at;           // start segment of every piece, + n_seg
+    {
+        int64_t first = (1000 / group_size) * group_size;
+        if (first < group_size) first = group_size;
+        if (first > chunk || n_seg < 2 * first) first = chunk;
+        for (int64_t s0 = 0; s0 < n_seg; s0 += (s0 == 0 ? first : chunk)) piece_at.push_back(s0);
+        piece_at.push_back(n_seg);
+    }
+    const int n_pieces = static_cast<int>(piece_at.size()) - 1;
+    auto upload = [&](int i, int b) -> cudaError_t {      // piece i -> xin[b], on the copy stream
+        const int64_t s0 = piece_at[i], n = piece_at[i + 1] - s0;
         cudaError_t e = cudaStreamWaitEvent(s->copy_stream, s->ev_free[b], 0);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(s->xin[b], src + static_cast<size_t>(s0) * 8000 * elt, static_cast<size_t>(n) * 8000 * elt,
@@ -1120,11 +1132,10 @@ static int fingerprint_host(nafp_ctx* ctx, const void* x_host, bool pcm16, int64
     };
     // the copy stream starts behind everything already queued on the compute stream (it may still read xin[0/1])
     for (int b = 0; b < 2; ++b) NAFP_CUDA(cudaEventRecord(s->ev_free[b], ctx->stream));
-    if (n_seg > 0) NAFP_CUDA(upload(0, 0));
-    int b = 0;
-    for (int64_t s0 = 0; s0 < n_seg; s0 += chunk, b ^= 1) {
-        const int64_t n = n_seg - s0 < chunk ? n_seg - s0 : chunk;
-        if (s0 + chunk < n_seg) NAFP_CUDA(upload(s0 + chunk, b ^ 1));     // under this pass's kernels
+    if (n_pieces > 0) NAFP_CUDA(upload(0, 0));
+    for (int i = 0, b = 0; i < n_pieces; ++i, b ^= 1) {
+        const int64_t s0 = piece_at[i], n = piece_at[i + 1] - s0;
+        if (i + 1 < n_pieces) NAFP_CUDA(upload(i + 1, b ^ 1));     // under this piece's kernels
         NAFP_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev_up[b], 0));
         NAFP_TRY(fingerprint_dev(ctx, s->xin[b], pcm16, n, group_size, s->emb));
         NAFP_CUDA(cudaEventRecord(s->ev_free[b], ctx->stream));
