@@ -44,7 +44,10 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
 bool logmel_segment_norm(nafp_ctx* ctx);
 
 constexpr int ENC_LAYERS = 16;
-constexpr int ENC_CHUNK_MAX = 4000;    // most segments of one encoder pass (2.3 MB of activations each): at 1,000 the
+#ifndef NAFP_ENC_CHUNK_MAX
+#define NAFP_ENC_CHUNK_MAX 4000
+#endif
+constexpr int ENC_CHUNK_MAX = NAFP_ENC_CHUNK_MAX;    // most segments of one encoder pass (2.3 MB of activations each): at 1,000 the
                                        // six last layers have fewer tiles than the chip has SMs
 constexpr int ENC_CHUNK_MIN = 1000;    // the activation arena starts here and grows on demand (encoder_reserve)
 constexpr int EMB = 128;

@@ -223,7 +223,9 @@ flat_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // rate: with a static split the slowest CTA finished 35 % after the fastest), then the warm tiles again
     // (with thresholds), then the end marker.  The TMA producer draws the tiles and tells the MMA issuer and
     // the epilogue through bars->tile_of.
-    const int warm = (tune & 2) ? 1 : max(1, min(WARM_TILES, n_tiles / G));
+    // bits 8..11 of the tune word override the number of warm tiles (A/B measurements)
+    const int warm_cap = ((tune >> 8) & 15) ? ((tune >> 8) & 15) : WARM_TILES;
+    const int warm = (tune & 2) ? 1 : max(1, min(warm_cap, n_tiles / G));
 
     for (int i = threadIdx.x; i < NQ_MAX; i += blockDim.x) {
         lmax_s[i] = INT_MIN;

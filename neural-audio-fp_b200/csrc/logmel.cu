@@ -35,10 +35,19 @@ static_assert(2 * 64 * 9 >= 512, "Q must hold mag");
 struct LogmelState {
     float* melw = nullptr;     // [MAXTAPS][NMEL]
     int* start = nullptr;      // [NMEL]
+    float* tab = nullptr;      // window + twiddle tables (TAB_* offsets), computed in double on the host
     int32_t* gmax = nullptr;   // [2][cap] ordered-int group maxima, then group minima
     int64_t gmax_cap = 0;
     bool segment_norm = false; // MODEL.FEAT == 'melspec_maxnorm' (melspectrogram.py:110-111)
 };
+
+// Window and twiddle factors come from tables (computed once in double precision): every thread needs 16 window values
+// and 24 twiddles, and 40 sincospif calls per thread were a fifth of the kernel's instructions.
+constexpr int TAB_WIN = 0;                  // [1024]        periodic Hann window
+constexpr int TAB_TW1 = 1024;               // [512][2]      e^{-2 pi i k / 512}
+constexpr int TAB_TW2 = TAB_TW1 + 2 * 512;  // [64][2]       e^{-2 pi i k / 64}
+constexpr int TAB_TWP = TAB_TW2 + 2 * 64;   // [512][2]      e^{-2 pi i k / 1024}
+constexpr int TAB_FLOATS = TAB_TWP + 2 * 512;
 
 // ---- 8-point FFT, natural order in and out
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -69,13 +78,6 @@ __device__ __forceinline__ void fft8(float2 (&a)[8]) {
     a[0] = b0; a[2] = b1; a[4] = b2; a[6] = b3;
     a[1] = b4; a[3] = b5; a[5] = b6; a[7] = b7;
 }
-// e^{-2 pi i num / den}
-__device__ __forceinline__ float2 twiddle(int num, int den) {
-    float s, c;
-    sincospif(2.0f * static_cast<float>(num) / static_cast<float>(den), &s, &c);
-    return make_float2(c, -s);
-}
-
 template <typename TIn>
 __device__ __forceinline__ float to_sample(TIn v);
 template <>
@@ -86,7 +88,7 @@ __device__ __forceinline__ float to_sample<int16_t>(int16_t v) { return static_c
 template <typename TIn>
 __global__ void __launch_bounds__(256, 2)
 logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, const float* __restrict__ melw,
-              const int* __restrict__ start, float* __restrict__ out, int32_t* __restrict__ gmax,
+              const int* __restrict__ start, const float* __restrict__ tab, float* __restrict__ out, int32_t* __restrict__ gmax,
               int32_t* __restrict__ gmin, const int64_t* __restrict__ seg_off, const int32_t* __restrict__ seg_valid) {
     extern __shared__ float smem[];
     float* xs = smem;                                  // [PADDED]
@@ -116,14 +118,12 @@ logmel_kernel(const TIn* __restrict__ x, int64_t n_seg, int64_t group_size, cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int m0 = 2 * (t + 64 * j);
-        float s, c;
-        sincospif(2.0f * m0 / 1024.0f, &s, &c);
-        win[2 * j] = 0.5f - 0.5f * c;
-        sincospif(2.0f * (m0 + 1) / 1024.0f, &s, &c);
-        win[2 * j + 1] = 0.5f - 0.5f * c;
-        tw1[j] = twiddle((t * j) & 511, 512);
-        tw2[j] = twiddle(((t >> 3) * j) & 63, 64);
-        twp[j] = twiddle(t + 64 * j, 1024);
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(tab + TAB_WIN + m0));
+        win[2 * j] = w2.x;
+        win[2 * j + 1] = w2.y;
+        tw1[j] = __ldg(reinterpret_cast<const float2*>(tab + TAB_TW1) + ((t * j) & 511));
+        tw2[j] = __ldg(reinterpret_cast<const float2*>(tab + TAB_TW2) + (((t >> 3) * j) & 63));
+        twp[j] = __ldg(reinterpret_cast<const float2*>(tab + TAB_TWP) + (t + 64 * j));
     }
 
     float* P = grp + g * GRP_FLOATS;       // S (re rows 0..7, im rows 8..15, stride S_LD)  /  Z (re[512], im[512])
@@ -304,6 +304,22 @@ static int logmel_init(nafp_ctx* ctx) {
         st[f] = first;
     }
     LogmelState* s = new LogmelState();
+    {
+        std::vector<float> tab(TAB_FLOATS);
+        const double pi = 3.14159265358979323846;
+        for (int i = 0; i < 1024; ++i) tab[TAB_WIN + i] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * pi * i / 1024.0));
+        auto fill = [&](int off, int den, int count) {          // e^{-2 pi i k / den}, k < count
+            for (int k = 0; k < count; ++k) {
+                tab[off + 2 * k] = static_cast<float>(std::cos(2.0 * pi * k / den));
+                tab[off + 2 * k + 1] = static_cast<float>(-std::sin(2.0 * pi * k / den));
+            }
+        };
+        fill(TAB_TW1, 512, 512);
+        fill(TAB_TW2, 64, 64);
+        fill(TAB_TWP, 1024, 512);
+        NAFP_CUDA(cudaMalloc(&s->tab, tab.size() * sizeof(float)));
+        NAFP_CUDA(cudaMemcpy(s->tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     NAFP_CUDA(cudaMalloc(&s->melw, w.size() * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->start, st.size() * sizeof(int)));
     NAFP_CUDA(cudaMemcpy(s->melw, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -318,6 +334,7 @@ void logmel_destroy(nafp_ctx* ctx) {
     if (!ctx->logmel) return;
     cudaFree(ctx->logmel->melw);
     cudaFree(ctx->logmel->start);
+    cudaFree(ctx->logmel->tab);
     if (ctx->logmel->gmax) cudaFree(ctx->logmel->gmax);
     delete ctx->logmel;
     ctx->logmel = nullptr;
@@ -352,10 +369,10 @@ int logmel_run(nafp_ctx* ctx, const void* x_dev, bool pcm16, int64_t n_seg, int6
     }
     if (pcm16)
         logmel_kernel<int16_t><<<static_cast<unsigned>(n_seg), 256, LOGMEL_SMEM, ctx->stream>>>(
-            static_cast<const int16_t*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, gmin, seg_off, seg_valid);
+            static_cast<const int16_t*>(x_dev), n_seg, group_size, s->melw, s->start, s->tab, mel_dev, s->gmax, gmin, seg_off, seg_valid);
     else
         logmel_kernel<float><<<static_cast<unsigned>(n_seg), 256, LOGMEL_SMEM, ctx->stream>>>(
-            static_cast<const float*>(x_dev), n_seg, group_size, s->melw, s->start, mel_dev, s->gmax, gmin, seg_off, seg_valid);
+            static_cast<const float*>(x_dev), n_seg, group_size, s->melw, s->start, s->tab, mel_dev, s->gmax, gmin, seg_off, seg_valid);
     ctx->launches += 2;
     if (finish) {
         const int64_t n4 = n_seg * (NMEL * NFRAMES / 4);

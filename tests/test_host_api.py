@@ -145,3 +145,16 @@ def test_cli_limits_are_checked_up_front():
     for args in (('l2', [1, 33], 20), ('l2', [19], 60), ('ivfpq', [1], 110), ('ivfpq-rr', [1], 40), ('l2', [], 20)):
         with pytest.raises(ValueError):
             _check_limits(*args)
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_profiles():
+    """bench.py's `roofline.traffic` is parsed from the ncu summaries under profiles/, not typed in."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    scan, f1 = bench.ncu_traffic("flat_scan_kernel", "r*_prof_scan*summary.csv")
+    assert f1 and f1.startswith("profiles/r2_") and 14.3e9 < scan < 15.5e9          # 56,029,500 rows x 256 B = 14.34 GB algorithmic
+    mel, f2 = bench.ncu_traffic("logmel_kernel", "r*_prof_logmel*summary.csv")
+    assert f2 and 1.0e8 < mel < 4.0e8                                                # 4,000 segments x 64,768 B = 0.26 GB algorithmic
+    assert bench.ncu_traffic("no_such_kernel", "r*_prof_scan*summary.csv") == (None, None)
