@@ -1367,6 +1367,10 @@ int nafp_index_profile_scans(nafp_index* idx, int enable, double* total_ms, int6
 int nafp_index_last_search_stats(nafp_index* idx, int64_t* out4) {
     NAFP_REQUIRE(idx && out4, NAFP_ERR_INVALID, "nafp_index_last_search_stats: bad arguments");
     for (int i = 0; i < 8; ++i) out4[i] = 0;
+    if (idx->ivf && idx->type != NAFP_INDEX_IVF_FLAT) {     // IVF-PQ: rows searched, rows answered by the LUT kernel, list-major work items / tiles
+        ivfpq_take_stats(idx, out4);
+        return NAFP_OK;
+    }
     if (!idx->stats) return NAFP_OK;
     unsigned long long h[8];
     NAFP_CUDA(cudaMemcpyAsync(h, idx->stats, sizeof(h), cudaMemcpyDeviceToHost, idx->ctx->stream));

@@ -85,4 +85,5 @@ void ivfpq_destroy(nafp_index* idx);
 int ivfpq_train(nafp_index* idx, const float* x_host, int64_t n, int64_t seed);
 int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n);
 int ivfpq_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev);
+void ivfpq_take_stats(nafp_index* idx, int64_t* out8);
 }  // namespace nafp

@@ -22,72 +22,16 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
 #include <vector>
 
-#include "index.h"
+#include "ivfpq.h"
 #include "ptx.cuh"
 
 namespace nafp {
-
-constexpr int PQ_MAX_M = 64;
-constexpr int PQ_KSUB = 256;
-constexpr int IVF_MAX_NLIST = 1024;
-constexpr int REFINE_M = 4, REFINE_KSUB = 16, REFINE_DSUB = 32, REFINE_KFACTOR = 4;
-constexpr int IVF_SCAN_CAP = 512;         // candidate buffer per (query, list) CTA: two 512-key sorts per list instead of two 1024-key ones
-
-struct IvfPq {
-    int nlist = 256, m = 64, dsub = 2;
-    bool flat_lists = false;      // IVF-Flat: the lists hold the stored rows themselves (no product quantizer)
-    bool trained = false;
-    float* coarse = nullptr;      // [nlist][128]
-    float* pq = nullptr;          // [m][256][dsub]
-    int32_t* assign = nullptr;    // [cap] list of every row (row order)
-    uint8_t* codes = nullptr;     // [cap][m]
-    int64_t cap = 0;
-    // list-sorted copy
-    bool dirty = true;
-    uint8_t* lcodes = nullptr;    // [n][m]
-    int32_t* lids = nullptr;      // [n]
-    int32_t* loff = nullptr;      // [nlist + 1]
-    int64_t sorted_cap = 0;
-    // IVFPQR (index_type 'ivfpq-rr', get_index_faiss.py:75-85): second-level product quantizer of the first level's
-    // residual x - xhat, M_refine 4 sub-spaces of 32 dims x 16 centroids (4 bit) = 2 bytes per row; the search asks the
-    // IVF-PQ for k * k_factor (faiss default 4) candidates and re-ranks them by |q - (xhat + rhat)|^2
-    bool refine = false;
-    float* rpq = nullptr;         // [4][16][32]
-    uint8_t* rcodes = nullptr;    // [cap][2]: nibbles (sub 0 | sub 1 << 4), (sub 2 | sub 3 << 4)
-    float* refD = nullptr;        // [nq_cap][REFINE_K]
-    int64_t* refI = nullptr;
-    int64_t ref_nq = 0;
-    // search scratch
-    int32_t* probes = nullptr;    // [nq_cap][nprobe_cap]
-    float* partD = nullptr;       // [nprobe][nq_cap][k]
-    int64_t* partI = nullptr;
-    int64_t scratch_nq = 0;
-    int scratch_nprobe = 0, scratch_k = 0;
-    // reconstruction path: ADC(q, code) = |q - xhat|^2 with xhat = coarse[list] + pq[m][code_m], so the IVF-PQ
-    // answer is the EXACT nearest-neighbour search over the reconstructed rows restricted to the probed
-    // lists.  B200 has the HBM to keep xhat resident: a flat index over it lets the tensor-core scan replace
-    // nq * nprobe * |list| * M shared-memory LUT gathers; the LUT kernel answers what the filter cannot prove.
-    nafp_index* recon = nullptr;  // flat index over xhat, same row order
-    float* xhat_tmp = nullptr;    // [RECON_CHUNK][128] decode staging
-    float* candD = nullptr;       // [nq_cap][RECON_K]
-    int64_t* candI = nullptr;
-    int64_t cand_nq = 0;
-    int32_t* probes_all = nullptr;    // [nq][nprobe] of the whole call
-    int64_t probes_all_elems = 0;
-    int32_t* redo_rows = nullptr; // query rows the filter could not answer, + counter at [cap]
-    float* redo_q = nullptr;      // gathered copies of those rows, and their results
-    float* redo_D = nullptr;
-    int64_t* redo_I = nullptr;
-    int64_t redo_cap = 0;
-    unsigned long long lut_rows = 0;      // rows answered by the LUT kernel since creation (statistics)
-};
-constexpr int RECON_K = 64;               // candidates fetched from the flat scan per query row
-constexpr int64_t RECON_CHUNK = 1 << 20;  // rows decoded per add step
 
 // ------------------------------------------------------------------------------------------ k-means
 // nearest centroid of `dim`-dimensional points (row stride `ld` floats); one warp per point, lane l
@@ -322,8 +266,15 @@ __global__ void ivf_scatter_kernel(const int32_t* __restrict__ assign, const uin
             lids[pos] = static_cast<int32_t>(i);
             if (codes) {                          // IVF-Flat lists carry row ids only
                 const uint4* src = reinterpret_cast<const uint4*>(codes + i * m);
-                uint4* dst = reinterpret_cast<uint4*>(lcodes + pos * m);
-                for (int v = 0; v < m / 16; ++v) dst[v] = src[v];
+                for (int v = 0; v < m / 16; ++v) {
+                    const uint4 cw = src[v];
+                    const uint32_t wds[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            lcodes[lcode_off(pos, v * 16 + t * 4 + b, m)] = static_cast<uint8_t>(wds[t] >> (8 * b));
+                }
             }
         }
     }
@@ -349,7 +300,7 @@ __global__ void ivfpq_probe_kernel(const float* __restrict__ q, int64_t nq, cons
             const float* cr = coarse + static_cast<int64_t>(c) * D128;
             for (int j = 0; j < D128; ++j) {
                 const float v = qs[w][j] - __ldg(cr + j);
-                acc += v * v;
+                acc = fmaf(v, v, acc);
             }
         }
         d[t] = acc;
@@ -373,27 +324,13 @@ __global__ void ivfpq_probe_kernel(const float* __restrict__ q, int64_t nq, cons
     }
 }
 
-__device__ void block_sort_asc_u64(uint64_t* keys, int n) {
-    for (int k = 2; k <= n; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t a = keys[i], b = keys[ixj];
-                    const bool asc = (i & k) == 0;
-                    if (asc ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-}
-
 // CTA (probe p, query row i): LUT T[m][c] = |(q - c_l)_m - pq_m[c]|^2 in shared memory, ADC scan of list l
 __global__ void __launch_bounds__(256)
 ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ coarse,
                   const float* __restrict__ pq, int m, int dsub, const int32_t* __restrict__ probes, int nprobe,
                   const uint8_t* __restrict__ lcodes, const int32_t* __restrict__ lids, const int32_t* __restrict__ loff,
-                  int k, int64_t label_offset, int64_t n_search, float* __restrict__ partD, int64_t* __restrict__ partI) {
+                  const int32_t* __restrict__ lend, int k, int64_t label_offset, int64_t n_search, float* __restrict__ partD,
+                  int64_t* __restrict__ partI) {
     extern __shared__ float lut[];                          // [m][256]
     __shared__ uint64_t buf[IVF_SCAN_CAP];
     __shared__ int cnt_s;
@@ -404,7 +341,7 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
     const int l = probes[i * nprobe + p];
     float* outD = partD + (static_cast<int64_t>(p) * nq + i) * k;
     int64_t* outI = partI + (static_cast<int64_t>(p) * nq + i) * k;
-    const int64_t lo = l >= 0 ? loff[l] : 0, hi = l >= 0 ? loff[l + 1] : 0;
+    const int64_t lo = l >= 0 ? loff[l] : 0, hi = l >= 0 ? lend[l] : 0;
     if (hi <= lo) {
         for (int j = tid; j < k; j += blockDim.x) { outD[j] = INFINITY; outI[j] = -1; }
         return;
@@ -416,7 +353,8 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
             const int dim = sub * dsub + j;
             const float r = q[i * D128 + dim] - coarse[static_cast<int64_t>(l) * D128 + dim];
             const float t = r - pq[(static_cast<int64_t>(sub) * PQ_KSUB + c) * dsub + j];
-            d += t * t;
+            d = fmaf(t, t, d);            // (what the compiler contracts `d += t * t` to; spelled out because ivfpq_lm.cu's
+                                          // exact re-rank must round identically)
         }
         lut[e] = d;
     }
@@ -426,18 +364,19 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
     for (int64_t base = lo; base < hi; base += blockDim.x) {
         const int64_t pos = base + tid;
         if (pos < hi && lids[pos] < n_search) {          // rows past n_search are the halo of a row-sharded index
-            const uint4* cp = reinterpret_cast<const uint4*>(lcodes + pos * m);
+            // (the codes are stored tile-transposed for the list-major scan, lcode_off: the position's byte of every
+            // 4-byte word of its 4 * mlo-byte segment, one segment per group of 32 sub-quantizers)
+            const int mlo = m < 32 ? m : 32;
+            const uint8_t* seg = lcodes + lcode_off(pos & ~static_cast<int64_t>(3), 0, m);
+            const int sh = static_cast<int>(pos & 3) * 8;
             float d = 0.f;
-            for (int v = 0; v < m / 16; ++v) {
-                const uint4 cw = cp[v];
-                const uint32_t wds[4] = {cw.x, cw.y, cw.z, cw.w};
+            for (int kb = 0; kb < m / mlo; ++kb) {
+                const uint4* lp = reinterpret_cast<const uint4*>(seg + kb * (LIST_TILE * mlo));
+                for (int v = 0; v < mlo / 4; ++v) {
+                    const uint4 cw = lp[v];
+                    const uint32_t wds[4] = {cw.x, cw.y, cw.z, cw.w};
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int sub = v * 16 + t * 4 + b;
-                        d += lut[sub * PQ_KSUB + ((wds[t] >> (8 * b)) & 255u)];
-                    }
+                    for (int b = 0; b < 4; ++b) d += lut[(kb * mlo + 4 * v + b) * PQ_KSUB + ((wds[b] >> sh) & 255u)];
                 }
             }
             const uint64_t key = (static_cast<uint64_t>(__float_as_uint(d)) << 32) | static_cast<uint32_t>(lids[pos]);
@@ -475,7 +414,7 @@ ivfpq_scan_kernel(const float* __restrict__ q, int64_t nq, const float* __restri
 __global__ void __launch_bounds__(256)
 ivfflat_scan_kernel(const float* __restrict__ q, int64_t nq, const int32_t* __restrict__ probes, int nprobe,
                     const float* __restrict__ x32, const int32_t* __restrict__ lids, const int32_t* __restrict__ loff,
-                    int k, int64_t label_offset, int64_t n_search, float* __restrict__ partD, int64_t* __restrict__ partI) {
+                    const int32_t* __restrict__ lend, int k, int64_t label_offset, int64_t n_search, float* __restrict__ partD, int64_t* __restrict__ partI) {
     __shared__ uint64_t buf[IVF_SCAN_CAP];
     __shared__ int cnt_s;
     __shared__ unsigned long long thr_s;
@@ -485,7 +424,7 @@ ivfflat_scan_kernel(const float* __restrict__ q, int64_t nq, const int32_t* __re
     const int l = probes[i * nprobe + p];
     float* outD = partD + (static_cast<int64_t>(p) * nq + i) * k;
     int64_t* outI = partI + (static_cast<int64_t>(p) * nq + i) * k;
-    const int64_t lo = l >= 0 ? loff[l] : 0, hi = l >= 0 ? loff[l + 1] : 0;
+    const int64_t lo = l >= 0 ? loff[l] : 0, hi = l >= 0 ? lend[l] : 0;
     if (hi <= lo) {
         for (int j = tid; j < k; j += blockDim.x) { outD[j] = INFINITY; outI[j] = -1; }
         return;
@@ -751,6 +690,7 @@ int ivfflat_create(nafp_index* idx, int nlist) {
     idx->ivf = s;                  // before the first fallible call: nafp_index_destroy releases it
     NAFP_CUDA(cudaMalloc(&s->coarse, static_cast<size_t>(nlist) * D128 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->loff, (nlist + 1) * sizeof(int32_t)));
+    NAFP_CUDA(cudaMalloc(&s->lend, nlist * sizeof(int32_t)));
     return NAFP_OK;
 }
 
@@ -767,8 +707,15 @@ int ivfpq_create(nafp_index* idx, int nlist, int m, int nbits) {
     NAFP_CUDA(cudaMalloc(&s->coarse, static_cast<size_t>(nlist) * D128 * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->pq, static_cast<size_t>(m) * PQ_KSUB * s->dsub * sizeof(float)));
     NAFP_CUDA(cudaMalloc(&s->loff, (nlist + 1) * sizeof(int32_t)));
-    NAFP_CUDA(cudaMalloc(&s->xhat_tmp, static_cast<size_t>(RECON_CHUNK) * D128 * sizeof(float)));
-    NAFP_TRY(nafp_index_create(idx->ctx, NAFP_INDEX_FLAT_L2, D128, 0, 0, 8, &s->recon));
+    NAFP_CUDA(cudaMalloc(&s->lend, nlist * sizeof(int32_t)));
+    // search path: the list-major compressed-domain scan (ivfpq_lm.cu) unless NAFP_IVFPQ_PATH says otherwise; only
+    // the reconstruction path keeps a flat index over the decoded rows (772 B per row)
+    const char* e = getenv("NAFP_IVFPQ_PATH");
+    s->path = !e ? IVFPQ_PATH_LM : !strcmp(e, "recon") ? IVFPQ_PATH_RECON : !strcmp(e, "lut") ? IVFPQ_PATH_LUT : IVFPQ_PATH_LM;
+    if (s->path == IVFPQ_PATH_RECON) {
+        NAFP_CUDA(cudaMalloc(&s->xhat_tmp, static_cast<size_t>(RECON_CHUNK) * D128 * sizeof(float)));
+        NAFP_TRY(nafp_index_create(idx->ctx, NAFP_INDEX_FLAT_L2, D128, 0, 0, 8, &s->recon));
+    }
     return NAFP_OK;
 }
 
@@ -776,7 +723,8 @@ void ivfpq_destroy(nafp_index* idx) {
     IvfPq* s = idx->ivf;
     if (!s) return;
     if (s->recon) nafp_index_destroy(s->recon);
-    void* bufs[] = {s->coarse, s->pq, s->assign, s->codes, s->lcodes, s->lids, s->loff, s->probes, s->partD, s->partI,
+    ivfpq_lm_destroy(s);
+    void* bufs[] = {s->coarse, s->pq, s->assign, s->codes, s->lcodes, s->lids, s->loff, s->lend, s->probes, s->partD, s->partI,
                     s->xhat_tmp, s->candD, s->candI, s->probes_all, s->redo_rows, s->redo_q, s->redo_D, s->redo_I,
                     s->rpq, s->rcodes, s->refD, s->refI};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -886,6 +834,7 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
     }
     NAFP_CUDA(cudaGetLastError());
     s->dirty = true;
+    if (!s->recon) return NAFP_OK;
     NAFP_TRY(index_reserve(s->recon, idx->cap));
     for (int64_t r0 = 0; r0 < n; r0 += RECON_CHUNK) {
         const int64_t nc = n - r0 < RECON_CHUNK ? n - r0 : RECON_CHUNK;
@@ -897,21 +846,22 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
     return NAFP_OK;
 }
 
-static int build_lists(nafp_index* idx) {
+int build_lists(nafp_index* idx) {
     IvfPq* s = idx->ivf;
     nafp_ctx* ctx = idx->ctx;
     const int64_t n = idx->n;
     if (!s->dirty) return NAFP_OK;
-    if (s->sorted_cap < n) {
+    const int64_t need = idx->cap + static_cast<int64_t>(LIST_TILE) * s->nlist;      // every list is padded to whole tiles
+    if (s->sorted_cap < need) {
         if (s->lcodes) cudaFree(s->lcodes);
         if (s->lids) cudaFree(s->lids);
         s->lcodes = nullptr; s->lids = nullptr; s->sorted_cap = 0;
-        if (!s->flat_lists) NAFP_CUDA(cudaMalloc(&s->lcodes, static_cast<size_t>(idx->cap) * s->m));
-        NAFP_CUDA(cudaMalloc(&s->lids, static_cast<size_t>(idx->cap) * sizeof(int32_t)));
-        s->sorted_cap = idx->cap;
+        if (!s->flat_lists) NAFP_CUDA(cudaMalloc(&s->lcodes, static_cast<size_t>(need) * s->m));
+        NAFP_CUDA(cudaMalloc(&s->lids, static_cast<size_t>(need) * sizeof(int32_t)));
+        s->sorted_cap = need;
     }
     const int nchunks = static_cast<int>((n + SORT_CHUNK - 1) / SORT_CHUNK);
-    std::vector<int32_t> off(s->nlist + 1, 0);
+    std::vector<int32_t> off(s->nlist + 1, 0), end(s->nlist, 0);
     if (nchunks > 0) {
         int32_t* hist = nullptr;
         int64_t* base = nullptr;
@@ -934,8 +884,14 @@ static int build_lists(nafp_index* idx) {
                 b[static_cast<size_t>(l) * nchunks + c] = run;
                 run += h[static_cast<size_t>(l) * nchunks + c];
             }
+            end[l] = static_cast<int32_t>(run);
+            run = (run + LIST_TILE - 1) / LIST_TILE * LIST_TILE;
         }
         off[s->nlist] = static_cast<int32_t>(run);
+        NAFP_REQUIRE(run <= s->sorted_cap && run < (1ll << 31), NAFP_ERR_UNSUPPORTED, "ivf lists: %lld padded positions", static_cast<long long>(run));
+        // padding positions: row id -1, code 0
+        NAFP_CUDA(cudaMemsetAsync(s->lids, 0xFF, static_cast<size_t>(run) * sizeof(int32_t), ctx->stream));
+        if (!s->flat_lists) NAFP_CUDA(cudaMemsetAsync(s->lcodes, 0, static_cast<size_t>(run) * s->m, ctx->stream));
         NAFP_CUDA(cudaMemcpyAsync(base, b.data(), b.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         ivf_scatter_kernel<<<nchunks, 32, 0, ctx->stream>>>(s->assign, s->codes, n, s->nlist, s->m, base, s->lcodes, s->lids);
         ctx->launches += 2;
@@ -943,6 +899,10 @@ static int build_lists(nafp_index* idx) {
         NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     NAFP_CUDA(cudaMemcpy(s->loff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    NAFP_CUDA(cudaMemcpy(s->lend, end.data(), end.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    s->h_loff = off;
+    s->h_lend = end;
+    s->lists_version++;
     s->dirty = false;
     return NAFP_OK;
 }
@@ -951,7 +911,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ D_all, const int64_t
                                   int k, float* __restrict__ D_out, int64_t* __restrict__ I_out);
 
 // the reference formulation: per (query row, probed list) LUT + ADC scan of the list's codes
-static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
+int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev) {
     IvfPq* s = idx->ivf;
     nafp_ctx* ctx = idx->ctx;
     if (nq == 0) return NAFP_OK;
@@ -983,10 +943,10 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
         ivfpq_probe_kernel<<<static_cast<unsigned>((nc + 7) / 8), 256, 0, ctx->stream>>>(qp, nc, s->coarse, s->nlist, nprobe, s->probes);
         if (s->flat_lists)
             ivfflat_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, 0, ctx->stream>>>(
-                qp, nc, s->probes, nprobe, idx->x32, s->lids, s->loff, k, idx->label_offset, n_search, s->partD, s->partI);
+                qp, nc, s->probes, nprobe, idx->x32, s->lids, s->loff, s->lend, k, idx->label_offset, n_search, s->partD, s->partI);
         else
             ivfpq_scan_kernel<<<dim3(nprobe, static_cast<unsigned>(nc)), 256, lut_bytes, ctx->stream>>>(
-                qp, nc, s->coarse, s->pq, s->m, s->dsub, s->probes, nprobe, s->lcodes, s->lids, s->loff, k, idx->label_offset,
+                qp, nc, s->coarse, s->pq, s->m, s->dsub, s->probes, nprobe, s->lcodes, s->lids, s->loff, s->lend, k, idx->label_offset,
                 n_search, s->partD, s->partI);
         topk_merge_kernel<<<static_cast<unsigned>(nc), 128, 0, ctx->stream>>>(s->partD, s->partI, nprobe, nc, k, D_dev + q0 * k,
                                                                               I_dev + q0 * k);
@@ -994,6 +954,46 @@ static int ivfpq_search_lut(nafp_index* idx, const float* q_dev, int64_t nq, int
     }
     NAFP_CUDA(cudaGetLastError());
     s->lut_rows += static_cast<unsigned long long>(nq);
+    return NAFP_OK;
+}
+
+void ivfpq_take_stats(nafp_index* idx, int64_t* out8) {
+    IvfPq* s = idx->ivf;
+    out8[0] = idx->host_rows;
+    out8[1] = static_cast<int64_t>(s->lut_rows);
+    ivfpq_lm_take_stats(s, &out8[2], &out8[3]);
+    idx->host_rows = idx->host_passes = 0;
+    s->lut_rows = 0;
+}
+
+// query rows a fast path could not answer: redo_rows[0 .. n) + the counter at redo_rows[redo_cap]
+int ivfpq_reserve_redo(nafp_index* idx, int64_t nq) {
+    IvfPq* s = idx->ivf;
+    if (s->redo_cap < nq) {
+        void* old[] = {s->redo_rows, s->redo_q, s->redo_D, s->redo_I};
+        for (void* b : old) if (b) cudaFree(b);
+        s->redo_rows = nullptr; s->redo_q = nullptr; s->redo_D = nullptr; s->redo_I = nullptr; s->redo_cap = 0;
+        NAFP_CUDA(cudaMalloc(&s->redo_rows, static_cast<size_t>(nq + 1) * sizeof(int32_t)));
+        s->redo_cap = nq;
+    }
+    return NAFP_OK;
+}
+// ... answered by the LUT scan of their probed lists, scattered back into D / I
+int ivfpq_redo_rows(nafp_index* idx, const float* q_dev, int32_t n_redo, int k, float* D_dev, int64_t* I_dev) {
+    IvfPq* s = idx->ivf;
+    nafp_ctx* ctx = idx->ctx;
+    if (!s->redo_q) {
+        NAFP_CUDA(cudaMalloc(&s->redo_q, static_cast<size_t>(s->redo_cap) * D128 * sizeof(float)));
+        NAFP_CUDA(cudaMalloc(&s->redo_D, static_cast<size_t>(s->redo_cap) * MAX_K * sizeof(float)));
+        NAFP_CUDA(cudaMalloc(&s->redo_I, static_cast<size_t>(s->redo_cap) * MAX_K * sizeof(int64_t)));
+    }
+    ivfpq_gather_q_kernel<<<static_cast<unsigned>((static_cast<int64_t>(n_redo) * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        q_dev, s->redo_rows, n_redo, s->redo_q);
+    NAFP_TRY(ivfpq_search_lut(idx, s->redo_q, n_redo, k, s->redo_D, s->redo_I));
+    ivfpq_scatter_kernel<<<static_cast<unsigned>((static_cast<int64_t>(n_redo) * k + 255) / 256), 256, 0, ctx->stream>>>(
+        s->redo_D, s->redo_I, s->redo_rows, n_redo, k, D_dev, I_dev);
+    ctx->launches += 2;
+    NAFP_CUDA(cudaGetLastError());
     return NAFP_OK;
 }
 
@@ -1036,7 +1036,12 @@ static int ivfpq_search_first_level(nafp_index* idx, const float* q_dev, int64_t
     NAFP_REQUIRE(k >= 1 && k <= MAX_K && nprobe * k <= 4096, NAFP_ERR_INVALID,
                  "ivfpq search: need k <= %d and nprobe*k <= 4096 (nprobe %d, k %d)", MAX_K, nprobe, k);
     if (!s->flat_lists) idx->host_rows += nq;          // (the flat scan of an IVF-Flat index counts its own rows)
-    if (k > RECON_K / 2 || nq >= (1ll << 31)) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
+    if (nq >= (1ll << 31)) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
+    if (!s->flat_lists) {
+        if (s->path == IVFPQ_PATH_LM && ivfpq_lm_supported(idx, k)) return ivfpq_search_lm(idx, q_dev, nq, k, D_dev, I_dev);
+        if (s->path != IVFPQ_PATH_RECON || !s->recon) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
+    }
+    if (k > RECON_K / 2) return ivfpq_search_lut(idx, q_dev, nq, k, D_dev, I_dev);
 
     // 1. exact top-RECON_K over the reconstructed rows (tensor-core scan + fp32 re-rank)
     if (s->cand_nq < nq) {
@@ -1054,13 +1059,7 @@ static int ivfpq_search_first_level(nafp_index* idx, const float* q_dev, int64_t
         s->probes_all_elems = nq * nprobe;
     }
     int32_t* probes_all = s->probes_all;
-    if (s->redo_cap < nq) {
-        void* old[] = {s->redo_rows, s->redo_q, s->redo_D, s->redo_I};
-        for (void* b : old) if (b) cudaFree(b);
-        s->redo_rows = nullptr; s->redo_q = nullptr; s->redo_D = nullptr; s->redo_I = nullptr; s->redo_cap = 0;
-        NAFP_CUDA(cudaMalloc(&s->redo_rows, static_cast<size_t>(nq + 1) * sizeof(int32_t)));
-        s->redo_cap = nq;
-    }
+    NAFP_TRY(ivfpq_reserve_redo(idx, nq));
     int32_t* redo_count = s->redo_rows + s->redo_cap;
     NAFP_CUDA(cudaMemsetAsync(redo_count, 0, sizeof(int32_t), ctx->stream));
     if (s->flat_lists) {               // the stored rows are the "reconstructions": scan the index itself
@@ -1084,20 +1083,7 @@ static int ivfpq_search_first_level(nafp_index* idx, const float* q_dev, int64_t
     NAFP_CUDA(cudaMemcpyAsync(&n_redo, redo_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     // 4. rows with fewer than k probed rows among their RECON_K nearest: the LUT scan of their lists
-    if (n_redo > 0) {
-        if (!s->redo_q) {
-            NAFP_CUDA(cudaMalloc(&s->redo_q, static_cast<size_t>(s->redo_cap) * D128 * sizeof(float)));
-            NAFP_CUDA(cudaMalloc(&s->redo_D, static_cast<size_t>(s->redo_cap) * MAX_K * sizeof(float)));
-            NAFP_CUDA(cudaMalloc(&s->redo_I, static_cast<size_t>(s->redo_cap) * MAX_K * sizeof(int64_t)));
-        }
-        ivfpq_gather_q_kernel<<<static_cast<unsigned>((static_cast<int64_t>(n_redo) * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            q_dev, s->redo_rows, n_redo, s->redo_q);
-        NAFP_TRY(ivfpq_search_lut(idx, s->redo_q, n_redo, k, s->redo_D, s->redo_I));
-        ivfpq_scatter_kernel<<<static_cast<unsigned>((static_cast<int64_t>(n_redo) * k + 255) / 256), 256, 0, ctx->stream>>>(
-            s->redo_D, s->redo_I, s->redo_rows, n_redo, k, D_dev, I_dev);
-        ctx->launches += 2;
-        NAFP_CUDA(cudaGetLastError());
-    }
+    if (n_redo > 0) NAFP_TRY(ivfpq_redo_rows(idx, q_dev, n_redo, k, D_dev, I_dev));
     return NAFP_OK;
 }
 
