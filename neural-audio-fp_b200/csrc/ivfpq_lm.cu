@@ -541,12 +541,19 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                         sc[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) - hh.z;
                         sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) - hh.w;
                     }
+                    // one vote per chunk on the hot path (vote -> branch latency was half of the epilogue's time with one per
+                    // 8 columns); the per-group votes run only inside the rare branch
+                    float mg[4];
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
-                        float m = fmaxf(fmaxf(sc[8 * g8], sc[8 * g8 + 1]), sc[8 * g8 + 2]);
-                        m = fmaxf(fmaxf(m, sc[8 * g8 + 3]), sc[8 * g8 + 4]);
-                        m = fmaxf(fmaxf(m, sc[8 * g8 + 5]), fmaxf(sc[8 * g8 + 6], sc[8 * g8 + 7]));
-                        if (__any_sync(0xffffffffu, m > thr)) {
+                        mg[g8] = fmaxf(fmaxf(sc[8 * g8], sc[8 * g8 + 1]), sc[8 * g8 + 2]);
+                        mg[g8] = fmaxf(fmaxf(mg[g8], sc[8 * g8 + 3]), sc[8 * g8 + 4]);
+                        mg[g8] = fmaxf(fmaxf(mg[g8], sc[8 * g8 + 5]), fmaxf(sc[8 * g8 + 6], sc[8 * g8 + 7]));
+                    }
+                    if (!__any_sync(0xffffffffu, fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3])) > thr)) continue;
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        if (__any_sync(0xffffffffu, mg[g8] > thr)) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float sj = sc[8 * g8 + j];
