@@ -513,7 +513,7 @@ def run_gpu(args):
     # ---- IVF-PQ (BASELINE configs[4]): the approximate index the reference builds for index_type "ivfpq"
     # (nlist 256, M 64, 8 bit, nprobe 40), host API incl. H2D / D2H
     def ivfpq_leg(rows_dummy, keep=False):
-        """Index build (k-means on a 1-in-N sample of the dummy rows, encode + decode of every row) and the timed
+        """Index build (k-means on a 1-in-N sample of the dummy rows, encoding of every row) and the timed
         evaluation job through the host API; the database is generated chunk by chunk on the device."""
         from nafp_b200.eval.utils.get_index import IVFPQ, Index
         t_ivf = time.time()
@@ -542,12 +542,21 @@ def run_gpu(args):
         def ivf_step():
             result["ivf"] = iidx.seq_match(query_host, test_ids, sl_host, K_PROBE)
 
+        iidx.last_search_stats()
         ms_ivf = time_steps(torch, dev, ivf_step, args.steps, args.warmup, barrier)
+        st = iidx.last_search_stats()
         ip = result["ivf"][0]
+        tiles = st["reranked"] / args.steps          # (for an IVF-PQ index: 128 x 128 tiles of the list-major scan)
         out = {"index": "IVFPQ nlist 256, M 64, 8 bit, nprobe 40", "db_rows": rows_dummy + N_DB,
                "value": n_queries / (ms_ivf * 1e-3), "unit": "queries/s", "ms_per_step": ms_ivf, "train_s": t_train,
                "add_s": t_add,
                "through": "host API (nafp_seq_match: H2D queries, D2H predictions inside the timed region)",
+               "path": "list-major compressed-domain tensor-core scan (csrc/ivfpq_lm.cu): codes decoded tile by tile in shared "
+                       "memory, bf16 tcgen05 scores, exact fp32 ADC re-rank + proof, LUT kernel for what is not proven",
+               "index_bytes_per_row": 140,           # 64 B codes in row order + 64 B in list order + list id + row id + h
+               "search_stats_per_step": {"query_rows": st["rows"] / args.steps, "rows_answered_by_lut_kernel": st["fallback_rows"] / args.steps,
+                                         "work_items": st["passes"] / args.steps, "tiles_128x128": tiles},
+               "mma_tflops_over_whole_step": tiles * 2 * 128 * 128 * 128 / (ms_ivf * 1e-3) / 1e12,
                "top1_hit_rate": [float(100.0 * np.mean(ip[:, si, 0] == test_ids + rows_dummy)) for si in range(len(SEQ_LENS))]}
         if keep:
             return out, iidx, train_rows
@@ -576,12 +585,51 @@ def run_gpu(args):
                                   "trained on the same 100,000 rows with the same seed as the GPU index",
                 "cores": native.threads(), "seconds": time.time() - t0}
 
+    def ivfpq_lut_leg(iidx):
+        """The kernel north_star names -- per (query row, probed list) a 64 x 256 fp32 look-up table in shared memory and
+        an ADC scan of the list's codes (ivfpq_scan_kernel, the fallback of the list-major path) -- timed alone on 256
+        query rows of the same 1 M-row index; algorithmic bytes = SURVEY 8(d): 68 B per (query row, probed row)."""
+        from nafp_b200.eval.utils.get_index import IVFPQ, Index
+        os.environ["NAFP_IVFPQ_PATH"] = "lut"
+        try:
+            lidx = Index(IVFPQ, 128, nlist=256, pq_m=64, pq_nbits=8, device=local_rank)
+        finally:
+            del os.environ["NAFP_IVFPQ_PATH"]
+        lidx.set_ivfpq_params(*iidx.ivfpq_params())
+        rows = 1_000_000
+        buf = torch.empty((rows, 128), dtype=torch.float32, device=dev)
+        check(lib.nafp_synth_fp_rows(ctx.h, 11, 0, rows, 59, 0.5, ctypes.c_void_p(buf.data_ptr())))
+        lidx.add_dev(buf.data_ptr(), rows)
+        lidx.add_dev(dbt.data_ptr(), N_DB)
+        lidx.nprobe = 40
+        del buf
+        nq = 256
+        qd = q_dev[:nq].contiguous()
+        Dd = torch.empty((nq, K_PROBE), dtype=torch.float32, device=dev)
+        Id = torch.empty((nq, K_PROBE), dtype=torch.int64, device=dev)
+
+        def lut_step():
+            lidx.search_dev(qd.data_ptr(), nq, K_PROBE, Dd.data_ptr(), Id.data_ptr())
+
+        ms = time_steps(torch, dev, lut_step, max(3, args.steps // 4), 3, barrier)
+        Dl, Il = iidx.search(qd.cpu().numpy(), K_PROBE)
+        probed_rows = 40.0 / 256.0 * (rows + N_DB)
+        return {"kernel": "ivfpq_scan_kernel (shared-memory LUT ADC scan, one CTA per (query row, probed list))",
+                "query_rows": nq, "ms_per_search": ms, "value": nq / (ms * 1e-3), "unit": "query rows/s",
+                "algorithmic_GBps": nq * probed_rows * 68 / (ms * 1e-3) / 1e9,
+                "lut_lookups_per_s": nq * probed_rows * 64 / (ms * 1e-3),
+                "ids_identical_to_list_major_path": bool((Il == Id.cpu().numpy()).all()),
+                "distances_identical_to_list_major_path": bool((Dl == Dd.cpu().numpy()).all())}
+
     ivf = None
     if world == 1 and not args.no_mini and not args.no_ivfpq and n_dummy >= 1_000_000:
         if args.no_cpu:
-            ivf = ivfpq_leg(1_000_000)
+            ivf, iidx_keep, train_rows = ivfpq_leg(1_000_000, keep=True)
+            ivf["lut_kernel"] = ivfpq_lut_leg(iidx_keep)
+            del iidx_keep
         else:
             ivf, iidx_keep, train_rows = ivfpq_leg(1_000_000, keep=True)
+            ivf["lut_kernel"] = ivfpq_lut_leg(iidx_keep)
             del iidx_keep
             orc = ivfpq_oracle_hit_rates(train_rows, 1_000_000)
             ivf["oracle"] = orc
@@ -591,8 +639,9 @@ def run_gpu(args):
     del sidx
     torch.cuda.empty_cache()
 
-    # BASELINE configs[4] at full size: one GPU holds it (94 GB); N > 1 row-shards it like the flat index (quantizers
-    # trained on rank 0 and broadcast, codes / lists / reconstructions local), same all-gather + merge + max all-reduce
+    # BASELINE configs[4] at full size: one GPU holds it (7.8 GB of index next to the 43 GB of exact rows the sequence
+    # scoring reads); N > 1 row-shards it like the flat index (quantizers trained on rank 0 and broadcast, codes / lists
+    # local), same all-gather + merge + max all-reduce
     ivf_full = None
     if world == 1 and not args.no_ivfpq_full and n_dummy > 1_000_000:
         ivf_full = ivfpq_leg(n_dummy)
@@ -616,6 +665,7 @@ def run_gpu(args):
         ivf_full = {"index": "IVFPQ nlist 256, M 64, 8 bit, nprobe 40, row-sharded", "db_rows": n_total,
                     "value": n_queries / (ms_sivf * 1e-3), "unit": "queries/s", "ms_per_step": ms_sivf, "train_s": t_train,
                     "add_s": t_add, "through": "device-resident queries (seq_match_dev), NCCL all-gather + max all-reduce",
+                    "path": "list-major compressed-domain tensor-core scan (csrc/ivfpq_lm.cu) on every rank's row block",
                     "top1_hit_rate": [float(100.0 * np.mean(sp[:, si, 0] == test_ids + n_dummy)) for si in range(len(SEQ_LENS))]}
         del sivf
 

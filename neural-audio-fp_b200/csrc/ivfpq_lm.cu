@@ -54,7 +54,7 @@ constexpr int LM_A_BYTES = 2 * LM_KB_BYTES;             // 32 KB
 constexpr int LM_B_BYTES = 2 * LM_KB_BYTES;             // 32 KB per stage
 constexpr int LM_TAB_BYTES = 64 * PQ_KSUB * 4;          // 64 KB: [sub-quantizer][code] -> two bf16
 constexpr int LM_LIST_BYTES = LM_Q * LM_KP * 8;         // 32 KB
-constexpr int LM_SMEM = 1024 + LM_A_BYTES + LM_STAGES * LM_B_BYTES + LM_TAB_BYTES + LM_LIST_BYTES + LM_HRING * LM_ROWS * 4 + 256;
+constexpr int LM_SMEM = 1024 + LM_A_BYTES + LM_STAGES * LM_B_BYTES + LM_TAB_BYTES + LM_LIST_BYTES + LM_HRING * LM_ROWS * 4 + 512;
 constexpr int64_t LM_CHUNK_Q = 32768;     // query rows per launch group (bounds the candidate buffer: 256 B per pair)
 static_assert(LM_ROWS == 128, "the epilogue reads four 32-column chunks per tile");
 static_assert(LM_Q == LM_ROWS, "the query block and the tile share the K-block size");
@@ -329,6 +329,7 @@ struct LmBars {
     uint64_t bempty[LM_STAGES];
     uint64_t afull[2];
     uint64_t aempty[2];
+    uint64_t hfull[LM_HRING];      // h_s slot written (4 decoder warps): the decoders' direct hand-off to the epilogue
     uint32_t tmem_base;
     int item;
 };
@@ -374,6 +375,7 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
             mbar_init(&bars->afull[a], 1);
             mbar_init(&bars->aempty[a], LM_EPI_WARPS);
         }
+        for (int a = 0; a < LM_HRING; ++a) mbar_init(&bars->hfull[a], LM_ROWS / 32);
         mbar_fence_init();
     }
     if (warp == LM_MMA_WARP) {
@@ -476,7 +478,12 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                 if (dt < LM_ROWS) h_s[(g & (LM_HRING - 1)) * LM_ROWS + dt] = hv;
                 fence_proxy_async_smem();          // this thread's tile bytes -> visible to the tensor core's (async) proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->bfull[s]);
+                if (lane == 0) {
+                    // (slot g & 3 is written again for tile g + 4, whose stage is free only after tile g + 2's MMAs, which wait
+                    // for the epilogue of tile g: never more than one phase ahead of the reader)
+                    if (dt < LM_ROWS) mbar_arrive(&bars->hfull[g & (LM_HRING - 1)]);
+                    mbar_arrive(&bars->bfull[s]);
+                }
             }
         } else if (warp == LM_MMA_WARP) {
             // ------------------------------------------------------------ MMA issuer
@@ -522,6 +529,7 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
             for (int t = 0; t < T; ++t, ++g) {
                 const int acc = g & 1;
                 mbar_wait_parked(&bars->afull[acc], (g >> 1) & 1);
+                mbar_wait_parked(&bars->hfull[g & (LM_HRING - 1)], (g >> 2) & 1);       // (already complete: the MMAs needed the same tile)
                 tc_fence_after();
                 const uint32_t hrow_u32 = smem_u32(h_s + (g & (LM_HRING - 1)) * LM_ROWS);
                 const uint32_t pos0 = static_cast<uint32_t>(lo + t * LM_ROWS);

@@ -253,3 +253,109 @@ def test_ivfpq_rr_same_quantizers_matches_oracle():
     for mode in ('hnsw', 'ivfpq-ondisk'):
         with pytest.raises(NotImplementedError, match='only available in CPU'):
             get_index(mode, dummy[:100], (100, 128), True, 1e7)
+
+
+# ------------------------------------------------------------------------------------------ list-major path (ivfpq_lm.cu)
+def _ivfpq_with_path(monkeypatch, path, params, parts, nprobe, nlist=256):
+    """An IVF-PQ index searched through `path` (NAFP_IVFPQ_PATH is read when the index is created)."""
+    from nafp_b200.eval.utils.get_index import IVFPQ, Index
+    monkeypatch.setenv("NAFP_IVFPQ_PATH", path)
+    g = Index(IVFPQ, 128, nlist=nlist, pq_m=64, pq_nbits=8)
+    g.set_ivfpq_params(*params)
+    for p in parts:
+        g.add(p)
+    g.nprobe = nprobe
+    return g
+
+
+def _trained_params(train, nlist=256, seed=5):
+    from nafp_b200.eval.utils.get_index import IVFPQ, Index
+    t = Index(IVFPQ, 128, nlist=nlist, pq_m=64, pq_nbits=8)
+    t.train(train, seed=seed)
+    return t.ivfpq_params()
+
+
+def test_ivfpq_three_search_paths_agree(monkeypatch):
+    """The default list-major tensor-core scan, the reconstruction path and the LUT kernel answer alike: the list-major
+    path re-scores its survivors with the LUT kernel's fp32 arithmetic, so its distances are bit-identical to the LUT
+    path's and its ids equal; none of its rows needed the fallback."""
+    from nafp_b200 import synth
+    dummy, db, query = synth.synth_search_set(60000, 1180, seed=23)
+    params = _trained_params(dummy[:40000])
+    idx = {p: _ivfpq_with_path(monkeypatch, p, params, (dummy, db), 40) for p in ("lm", "lut", "recon")}
+    q = query[:700]
+    res = {p: g.search(q, 20) for p, g in idx.items()}
+    st = idx["lm"].last_search_stats()
+    assert st["rows"] == len(q) and st["fallback_rows"] == 0 and st["passes"] > 0, st      # passes = list-major work items
+    assert idx["lut"].last_search_stats()["fallback_rows"] == len(q)
+    np.testing.assert_array_equal(res["lm"][0], res["lut"][0])
+    np.testing.assert_array_equal(res["lm"][1], res["lut"][1])
+    np.testing.assert_allclose(res["recon"][0], res["lut"][0], rtol=0, atol=2e-5)
+    assert (res["recon"][1] == res["lut"][1]).mean() > 0.98
+
+
+@pytest.mark.parametrize("n_rows,nlist,nprobe,k,nq", [(300, 64, 64, 5, 1), (300, 64, 1, 24, 3), (5000, 256, 40, 1, 130),
+                                                      (5000, 16, 16, 20, 257), (40, 8, 3, 24, 19)])
+def test_ivfpq_list_major_ragged_shapes(monkeypatch, n_rows, nlist, nprobe, k, nq):
+    """Empty and tiny lists, lists shorter than one tile, fewer rows than k, one query row, more than one block of query
+    rows per list: identical to the LUT kernel, and to the oracle within its tolerance."""
+    from nafp_b200 import synth
+    from oracle.ivfpq_index import IVFPQ as OracleIVFPQ
+    dummy, db, query = synth.synth_search_set(max(n_rows, 3000), 590, seed=29)
+    params = _trained_params(dummy[:3000], nlist=nlist)
+    rows = dummy[:n_rows]
+    a = _ivfpq_with_path(monkeypatch, "lm", params, (rows,), nprobe, nlist)
+    b = _ivfpq_with_path(monkeypatch, "lut", params, (rows,), nprobe, nlist)
+    q = query[:nq]
+    Da, Ia = a.search(q, k)
+    Db, Ib = b.search(q, k)
+    np.testing.assert_array_equal(Da, Db)
+    np.testing.assert_array_equal(Ia, Ib)
+    o = OracleIVFPQ(128, nlist, 64, 8)
+    o.set_params(*params)
+    o.add(rows)
+    o.nprobe = nprobe
+    Do, Io = o.search(q, k)
+    fin = np.isfinite(Do)
+    assert (np.isfinite(Da) == fin).all() and ((Ia < 0) == (Io < 0)).all()
+    np.testing.assert_allclose(Da[fin], Do[fin], rtol=0, atol=2e-5)
+    assert (Ia == Io).mean() >= 0.97
+
+
+def test_ivfpq_list_major_duplicates_go_to_the_lut_kernel(monkeypatch):
+    """60 identical rows next to a query: the 32-entry candidate list of their list ends in a tie, the proof fails, the
+    row is answered by the LUT kernel -- same ids (ties to the lower id) as the LUT path."""
+    from nafp_b200 import synth
+    dummy, db, query = synth.synth_search_set(20000, 590, seed=31)
+    params = _trained_params(dummy[:12000])
+    dup = np.repeat(db[7:8], 60, axis=0)
+    parts = (dummy, dup, db)
+    a = _ivfpq_with_path(monkeypatch, "lm", params, parts, 40)
+    b = _ivfpq_with_path(monkeypatch, "lut", params, parts, 40)
+    q = np.concatenate([db[7:8], query[:40]])
+    Da, Ia = a.search(q, 20)
+    Db, Ib = b.search(q, 20)
+    np.testing.assert_array_equal(Da, Db)
+    np.testing.assert_array_equal(Ia, Ib)
+    assert (Ia[0] == np.arange(20000, 20020)).all()           # the 20 lowest ids of the 61 tied rows
+    assert a.last_search_stats()["fallback_rows"] >= 1
+
+
+def test_ivfpq_list_major_respects_search_rows(monkeypatch):
+    """Rows past search_rows (the halo of a row-sharded index) are stored but never returned."""
+    from nafp_b200 import synth
+    dummy, db, query = synth.synth_search_set(20000, 590, seed=37)
+    params = _trained_params(dummy[:12000])
+    a = _ivfpq_with_path(monkeypatch, "lm", params, (dummy, db), 40)
+    b = _ivfpq_with_path(monkeypatch, "lut", params, (dummy, db), 40)
+    full = a.search(query[:64], 20)[1]
+    assert (full >= 20000).any()
+    for g in (a, b):
+        g.set_search_rows(20000)
+    Da, Ia = a.search(query[:64], 20)
+    Db, Ib = b.search(query[:64], 20)
+    assert (Ia < 20000).all()
+    np.testing.assert_array_equal(Da, Db)
+    np.testing.assert_array_equal(Ia, Ib)
+    a.set_search_rows(-1)
+    np.testing.assert_array_equal(a.search(query[:64], 20)[1], full)
