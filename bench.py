@@ -546,7 +546,8 @@ def run_gpu(args):
         ms_ivf = time_steps(torch, dev, ivf_step, args.steps, args.warmup, barrier)
         st = iidx.last_search_stats()
         ip = result["ivf"][0]
-        tiles = st["reranked"] / args.steps          # (for an IVF-PQ index: 128 x 128 tiles of the list-major scan)
+        n_run = args.steps + args.warmup             # the statistics cover the warm-up steps too
+        tiles = st["reranked"] / n_run               # (for an IVF-PQ index: 128 x 128 tiles of the list-major scan)
         out = {"index": "IVFPQ nlist 256, M 64, 8 bit, nprobe 40", "db_rows": rows_dummy + N_DB,
                "value": n_queries / (ms_ivf * 1e-3), "unit": "queries/s", "ms_per_step": ms_ivf, "train_s": t_train,
                "add_s": t_add,
@@ -554,8 +555,8 @@ def run_gpu(args):
                "path": "list-major compressed-domain tensor-core scan (csrc/ivfpq_lm.cu): codes decoded tile by tile in shared "
                        "memory, bf16 tcgen05 scores, exact fp32 ADC re-rank + proof, LUT kernel for what is not proven",
                "index_bytes_per_row": 140,           # 64 B codes in row order + 64 B in list order + list id + row id + h
-               "search_stats_per_step": {"query_rows": st["rows"] / args.steps, "rows_answered_by_lut_kernel": st["fallback_rows"] / args.steps,
-                                         "work_items": st["passes"] / args.steps, "tiles_128x128": tiles},
+               "search_stats_per_step": {"query_rows": st["rows"] / n_run, "rows_answered_by_lut_kernel": st["fallback_rows"] / n_run,
+                                         "work_items": st["passes"] / n_run, "tiles_128x128": tiles},
                "mma_tflops_over_whole_step": tiles * 2 * 128 * 128 * 128 / (ms_ivf * 1e-3) / 1e12,
                "top1_hit_rate": [float(100.0 * np.mean(ip[:, si, 0] == test_ids + rows_dummy)) for si in range(len(SEQ_LENS))]}
         if keep:
