@@ -554,7 +554,8 @@ def run_gpu(args):
                "through": "host API (nafp_seq_match: H2D queries, D2H predictions inside the timed region)",
                "path": "list-major compressed-domain tensor-core scan (csrc/ivfpq_lm.cu): codes decoded tile by tile in shared "
                        "memory, bf16 tcgen05 scores, exact fp32 ADC re-rank + proof, LUT kernel for what is not proven",
-               "index_bytes_per_row": 140,           # 64 B codes in row order + 64 B in list order + list id + row id + h
+               "index_bytes_per_row": 76,            # 64 B codes (list order, tile-transposed) + row id + h + list id; the row-order
+                                                     # staging copy of the codes is released when the lists are built
                "search_stats_per_step": {"query_rows": st["rows"] / n_run, "rows_answered_by_lut_kernel": st["fallback_rows"] / n_run,
                                          "work_items": st["passes"] / n_run, "tiles_128x128": tiles},
                "mma_tflops_over_whole_step": tiles * 2 * 128 * 128 * 128 / (ms_ivf * 1e-3) / 1e12,
@@ -640,7 +641,7 @@ def run_gpu(args):
     del sidx
     torch.cuda.empty_cache()
 
-    # BASELINE configs[4] at full size: one GPU holds it (7.8 GB of index next to the 43 GB of exact rows the sequence
+    # BASELINE configs[4] at full size: one GPU holds it (4.3 GB of index next to the 28.7 GB of exact rows the sequence
     # scoring reads); N > 1 row-shards it like the flat index (quantizers trained on rank 0 and broadcast, codes / lists
     # local), same all-gather + merge + max all-reduce
     ivf_full = None

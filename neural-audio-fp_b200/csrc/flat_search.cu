@@ -918,18 +918,22 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     __nv_bfloat16* x16 = nullptr;
     float* hn = nullptr;
     NAFP_CUDA(cudaMalloc(&x32, static_cast<size_t>(new_cap) * idx->d * sizeof(float)));
-    NAFP_CUDA(cudaMalloc(&x16, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16)));
-    NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap + SCAN_TILE) * sizeof(float)));
-    NAFP_CUDA(cudaMemsetAsync(x16, 0, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16), ctx->stream));
+    if (idx->scan_copy) {
+        NAFP_CUDA(cudaMalloc(&x16, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16)));
+        NAFP_CUDA(cudaMalloc(&hn, static_cast<size_t>(new_cap + SCAN_TILE) * sizeof(float)));
+        NAFP_CUDA(cudaMemsetAsync(x16, 0, static_cast<size_t>(new_cap) * idx->d * sizeof(__nv_bfloat16), ctx->stream));
+    }
     if (idx->n > 0) {
         NAFP_CUDA(cudaMemcpyAsync(x32, idx->x32, static_cast<size_t>(idx->n) * idx->d * sizeof(float),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
-        NAFP_CUDA(cudaMemcpyAsync(x16, idx->x16, static_cast<size_t>(idx->n) * idx->d * sizeof(__nv_bfloat16),
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
-        NAFP_CUDA(cudaMemcpyAsync(hn, idx->hn, static_cast<size_t>(idx->n) * sizeof(float),
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        if (idx->scan_copy) {
+            NAFP_CUDA(cudaMemcpyAsync(x16, idx->x16, static_cast<size_t>(idx->n) * idx->d * sizeof(__nv_bfloat16),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+            NAFP_CUDA(cudaMemcpyAsync(hn, idx->hn, static_cast<size_t>(idx->n) * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     }
-    {
+    if (idx->scan_copy) {
         const int64_t cnt = new_cap + SCAN_TILE - idx->n;
         const int threads = 256;
         const int64_t blocks = (cnt + threads - 1) / threads;
@@ -945,6 +949,7 @@ int index_reserve(nafp_index* idx, int64_t n_total) {
     idx->x16 = x16;
     idx->hn = hn;
     idx->cap = new_cap;
+    if (!idx->scan_copy) return NAFP_OK;
     // DB tensor map: [cap rows][128 bf16], box 64 columns x 128 rows, 128-byte swizzle
     const uint64_t dims[2] = {static_cast<uint64_t>(idx->d), static_cast<uint64_t>(new_cap)};
     const uint64_t strides[2] = {2, static_cast<uint64_t>(idx->d) * 2};
@@ -966,13 +971,15 @@ int flat_add_dev(nafp_index* idx, const float* x, int64_t n, bool src_is_host) {
     }
     NAFP_CUDA(cudaMemcpyAsync(idx->x32 + idx->n * idx->d, x, static_cast<size_t>(n) * idx->d * sizeof(float),
                               src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
-    const int threads = 256;
-    int64_t blocks = (n * 32 + threads - 1) / threads;
-    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    flat_convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(idx->x32, idx->x16, idx->hn,
-                                                                                        idx->maxn2, idx->n, n);
-    ctx->launches++;
-    NAFP_CUDA(cudaGetLastError());
+    if (idx->scan_copy) {
+        const int threads = 256;
+        int64_t blocks = (n * 32 + threads - 1) / threads;
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        flat_convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(idx->x32, idx->x16, idx->hn,
+                                                                                            idx->maxn2, idx->n, n);
+        ctx->launches++;
+        NAFP_CUDA(cudaGetLastError());
+    }
     if (src_is_host) NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
     idx->n += n;
     return NAFP_OK;
@@ -1079,6 +1086,7 @@ int flat_search_dev(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
     nafp_ctx* ctx = idx->ctx;
     NAFP_REQUIRE(k >= 1 && k <= MAX_K, NAFP_ERR_INVALID, "search: k=%d outside [1,%d]", k, MAX_K);
     NAFP_REQUIRE(idx->d == D128, NAFP_ERR_UNSUPPORTED, "search: d=%d (the tensor-core scan is built for d=128)", idx->d);
+    NAFP_REQUIRE(idx->scan_copy, NAFP_ERR_STATE, "search: this index keeps no bf16 scan copy of its rows (IVF-PQ types)");
     NAFP_REQUIRE(nq < (1ll << 31), NAFP_ERR_INVALID, "search: more than 2^31 query rows in one call");
     NAFP_CUDA(cudaSetDevice(ctx->device));
     NAFP_TRY(ensure_scratch(idx));
@@ -1158,6 +1166,7 @@ int nafp_index_create(nafp_ctx* ctx, int type, int d, int nlist, int pq_m, int p
     idx->ctx = ctx;
     idx->type = type;
     idx->d = d;
+    idx->scan_copy = type == NAFP_INDEX_FLAT_L2 || type == NAFP_INDEX_IVF_FLAT;
     if (cudaMalloc(&idx->maxn2, sizeof(int32_t)) != cudaSuccess ||
         cudaMemsetAsync(idx->maxn2, 0, sizeof(int32_t), ctx->stream) != cudaSuccess) {
         set_error("nafp_index_create: cudaMalloc failed");

@@ -33,6 +33,7 @@ struct nafp_index {
     __nv_bfloat16* x16 = nullptr;     // [cap][d] scan copy
     float* hn = nullptr;              // [cap + SCAN_TILE] 0.5*|x|^2, +inf for unused rows
     int32_t* maxn2 = nullptr;         // device scalar: bits of max |x|^2 (non-negative float)
+    bool scan_copy = true;            // x16 / hn exist (flat and IVF-Flat indexes; the IVF-PQ types search their codes)
     int64_t label_offset = 0;
     int64_t search_rows = -1;     // leading rows that take part in search (-1 = all); the rest are halo
     CUtensorMap tmap_db;

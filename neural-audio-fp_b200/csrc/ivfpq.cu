@@ -280,6 +280,16 @@ __global__ void ivf_scatter_kernel(const int32_t* __restrict__ assign, const uin
     }
 }
 
+// the inverse of the scatter: row-order codes from the lists (one thread per list position)
+__global__ void ivf_unscatter_kernel(const uint8_t* __restrict__ lcodes, const int32_t* __restrict__ lids, int64_t n_pos, int m,
+                                     uint8_t* __restrict__ codes) {
+    const int64_t pos = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pos >= n_pos) return;
+    const int32_t row = lids[pos];
+    if (row < 0) return;
+    for (int sub = 0; sub < m; ++sub) codes[static_cast<int64_t>(row) * m + sub] = lcodes[lcode_off(pos, sub, m)];
+}
+
 // ------------------------------------------------------------------------------------------ search
 // one warp per query row: the nprobe nearest coarse centroids, ascending (ties -> lower list id)
 __global__ void ivfpq_probe_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ coarse,
@@ -787,15 +797,23 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
     IvfPq* s = idx->ivf;
     nafp_ctx* ctx = idx->ctx;
     if (n == 0) return NAFP_OK;
-    if (idx->cap > s->cap) {
+    // The row-order copy of the codes is only the staging area of `add` (the lists are rebuilt from it): build_lists
+    // releases it (64 of the index's 140 B per row), the next add regenerates it from the lists.
+    const bool regen = !s->flat_lists && !s->codes && row0 > 0;
+    if (idx->cap > s->cap || regen) {
         int32_t* a = nullptr;
         uint8_t* c = nullptr;
         NAFP_CUDA(cudaMalloc(&a, static_cast<size_t>(idx->cap) * sizeof(int32_t)));
         if (!s->flat_lists) NAFP_CUDA(cudaMalloc(&c, static_cast<size_t>(idx->cap) * s->m));
         if (row0 > 0) {
             NAFP_CUDA(cudaMemcpyAsync(a, s->assign, static_cast<size_t>(row0) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-            if (!s->flat_lists)
+            if (regen) {
+                const int64_t n_pos = s->h_loff[s->nlist];
+                ivf_unscatter_kernel<<<static_cast<unsigned>((n_pos + 255) / 256), 256, 0, ctx->stream>>>(s->lcodes, s->lids, n_pos, s->m, c);
+                ctx->launches++;
+            } else if (!s->flat_lists) {
                 NAFP_CUDA(cudaMemcpyAsync(c, s->codes, static_cast<size_t>(row0) * s->m, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
             NAFP_CUDA(cudaStreamSynchronize(ctx->stream));
         }
         if (s->refine) {
@@ -904,6 +922,10 @@ int build_lists(nafp_index* idx) {
     s->h_lend = end;
     s->lists_version++;
     s->dirty = false;
+    if (!s->flat_lists && !s->refine && !s->recon && s->codes) {      // (IVFPQR re-ranks, the reconstruction path decodes, by row)
+        cudaFree(s->codes);
+        s->codes = nullptr;
+    }
     return NAFP_OK;
 }
 

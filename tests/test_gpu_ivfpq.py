@@ -359,3 +359,23 @@ def test_ivfpq_list_major_respects_search_rows(monkeypatch):
     np.testing.assert_array_equal(Ia, Ib)
     a.set_search_rows(-1)
     np.testing.assert_array_equal(a.search(query[:64], 20)[1], full)
+
+
+def test_ivfpq_add_after_search_rebuilds_lists_from_released_codes(monkeypatch):
+    """The row-order copy of the codes is released once the lists are built (76 B per row stay); a later add regenerates
+    it from the lists.  Same answers as an index that received all rows before its first search."""
+    from nafp_b200 import synth
+    dummy, db, query = synth.synth_search_set(30000, 1180, seed=43)
+    params = _trained_params(dummy[:20000])
+    a = _ivfpq_with_path(monkeypatch, "lm", params, (dummy[:17000],), 40)
+    first = a.search(query[:32], 20)[1]
+    assert (first < 17000).all()
+    a.add(dummy[17000:])
+    a.search(query[:8], 5)
+    a.add(db)
+    b = _ivfpq_with_path(monkeypatch, "lm", params, (dummy, db), 40)
+    Da, Ia = a.search(query[:200], 20)
+    Db, Ib = b.search(query[:200], 20)
+    np.testing.assert_array_equal(Da, Db)
+    np.testing.assert_array_equal(Ia, Ib)
+    assert a.ntotal == b.ntotal == 31180
