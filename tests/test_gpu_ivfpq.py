@@ -379,3 +379,19 @@ def test_ivfpq_add_after_search_rebuilds_lists_from_released_codes(monkeypatch):
     np.testing.assert_array_equal(Da, Db)
     np.testing.assert_array_equal(Ia, Ib)
     assert a.ntotal == b.ntotal == 31180
+
+
+def test_ivfpq_list_major_more_query_rows_than_one_launch_group(monkeypatch):
+    """33,000 query rows (> LM_CHUNK_Q = 32,768): the search runs in two launch groups; every row equals the LUT path's."""
+    from nafp_b200 import synth
+    dummy, db, query = synth.synth_search_set(6000, 590, seed=47)
+    params = _trained_params(dummy[:4000], nlist=64)
+    a = _ivfpq_with_path(monkeypatch, "lm", params, (dummy, db), 6, nlist=64)
+    b = _ivfpq_with_path(monkeypatch, "lut", params, (dummy, db), 6, nlist=64)
+    rng = np.random.default_rng(3)
+    q = query[rng.integers(0, len(query), 33000)] + 0.05 * rng.standard_normal((33000, 128)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    Da, Ia = a.search(q, 10)
+    Db, Ib = b.search(q, 10)
+    np.testing.assert_array_equal(Ia, Ib)
+    np.testing.assert_array_equal(Da, Db)
