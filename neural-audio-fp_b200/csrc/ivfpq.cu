@@ -225,6 +225,94 @@ ivfpq_encode_kernel(const float* __restrict__ x32, int64_t row0, int64_t n, cons
     }
 }
 
+// The same two steps for the reference's shape (nlist <= 256, M = 64, dsub = 2) with the tables in shared memory: the
+// 56 M-row build spent 13.5 s in the kernel above, whose 128 KB codebook thrashes L1.  Arithmetic and tie-breaking are
+// the kernel's above (fma chains, dimensions ascending, first minimum wins), so assignments and codes are identical.
+constexpr int ENC_NLIST = 256;
+constexpr int ENC_ASSIGN_SMEM = (D128 * ENC_NLIST + 8 * D128) * 4;          // transposed centroids + 8 rows
+constexpr int ENC_CODE_SMEM = PQ_KSUB * 64 * 8 + 8 * D128 * 4;              // [code][sub] float2 + 8 residual rows
+__global__ void __launch_bounds__(256)
+ivfpq_assign_smem_kernel(const float* __restrict__ x32, int64_t row0, int64_t n, const float* __restrict__ coarse, int nlist,
+                         int32_t* __restrict__ assign) {
+    extern __shared__ float esm[];
+    float* cs = esm;                                   // [dim][256 centroids]
+    float* xs = esm + D128 * ENC_NLIST;                // [8 warps][128]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < D128 * ENC_NLIST; e += blockDim.x) {
+        const int j = e / ENC_NLIST, c = e % ENC_NLIST;
+        cs[e] = c < nlist ? __ldg(coarse + static_cast<int64_t>(c) * D128 + j) : 0.f;
+    }
+    __syncthreads();
+    float* xr = xs + w * D128;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + w; r < n; r += static_cast<int64_t>(gridDim.x) * 8) {
+        __syncwarp();
+        reinterpret_cast<float4*>(xr)[lane] = reinterpret_cast<const float4*>(x32 + (row0 + r) * D128)[lane];
+        __syncwarp();
+        float d[ENC_NLIST / 32];
+#pragma unroll
+        for (int t = 0; t < ENC_NLIST / 32; ++t) d[t] = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < D128; ++j) {
+            const float xj = xr[j];
+            const float* cr = cs + j * ENC_NLIST + lane;
+#pragma unroll
+            for (int t = 0; t < ENC_NLIST / 32; ++t) {
+                const float v = xj - cr[32 * t];
+                d[t] = fmaf(v, v, d[t]);
+            }
+        }
+        float best = FLT_MAX;
+        int bi = INT_MAX;
+#pragma unroll
+        for (int t = 0; t < ENC_NLIST / 32; ++t)              // centroid lane + 32 t, ascending: the first minimum wins
+            if (lane + 32 * t < nlist && d[t] < best) { best = d[t]; bi = lane + 32 * t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) assign[row0 + r] = bi;
+    }
+}
+__global__ void __launch_bounds__(256)
+ivfpq_code_smem_kernel(const float* __restrict__ x32, int64_t row0, int64_t n, const float* __restrict__ coarse,
+                       const float* __restrict__ pq, const int32_t* __restrict__ assign, uint8_t* __restrict__ codes) {
+    extern __shared__ float esm[];
+    float2* pqs = reinterpret_cast<float2*>(esm);      // [code][sub]: lane = sub-quantizer reads consecutive 8 bytes
+    float* xs = esm + PQ_KSUB * 64 * 2;                // [8 warps][128] residuals
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < PQ_KSUB * 64; e += blockDim.x) {
+        const int c = e >> 6, sub = e & 63;
+        pqs[e] = __ldg(reinterpret_cast<const float2*>(pq) + sub * PQ_KSUB + c);
+    }
+    __syncthreads();
+    float* xr = xs + w * D128;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + w; r < n; r += static_cast<int64_t>(gridDim.x) * 8) {
+        const int64_t row = row0 + r;
+        const float4 cv = reinterpret_cast<const float4*>(coarse + static_cast<int64_t>(assign[row]) * D128)[lane];
+        float4 v = reinterpret_cast<const float4*>(x32 + row * D128)[lane];
+        v.x -= cv.x; v.y -= cv.y; v.z -= cv.z; v.w -= cv.w;
+        __syncwarp();
+        reinterpret_cast<float4*>(xr)[lane] = v;
+        __syncwarp();
+        const float a0 = xr[2 * lane], a1 = xr[2 * lane + 1];                 // sub-quantizer lane
+        const float b0 = xr[2 * (lane + 32)], b1 = xr[2 * (lane + 32) + 1];   // sub-quantizer lane + 32
+        float bda = FLT_MAX, bdb = FLT_MAX;
+        int bca = 0, bcb = 0;
+#pragma unroll 4
+        for (int c = 0; c < PQ_KSUB; ++c) {
+            const float2 pa = pqs[c * 64 + lane], pb = pqs[c * 64 + 32 + lane];
+            const float ta0 = a0 - pa.x, ta1 = a1 - pa.y, tb0 = b0 - pb.x, tb1 = b1 - pb.y;
+            const float da = fmaf(ta1, ta1, ta0 * ta0), db = fmaf(tb1, tb1, tb0 * tb0);
+            if (da < bda) { bda = da; bca = c; }
+            if (db < bdb) { bdb = db; bcb = c; }
+        }
+        codes[row * 64 + lane] = static_cast<uint8_t>(bca);
+        codes[row * 64 + 32 + lane] = static_cast<uint8_t>(bcb);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ inverted lists
 constexpr int SORT_CHUNK = 4096;     // rows per (single-warp) block of the stable counting sort
 
@@ -841,9 +929,20 @@ int ivfpq_add_rows(nafp_index* idx, int64_t row0, int64_t n) {
         return NAFP_OK;
     }
     int64_t blocks = (n + 7) / 8;
-    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    ivfpq_encode_kernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(idx->x32, row0, n, s->coarse, s->nlist, s->pq,
-                                                                              s->m, s->dsub, s->assign, s->codes);
+    if (s->nlist <= ENC_NLIST && s->m == 64 && s->dsub == 2) {
+        if (blocks > ctx->sm_count) blocks = ctx->sm_count;          // one block per SM: each loads its table once
+        NAFP_CUDA(cudaFuncSetAttribute(ivfpq_assign_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_ASSIGN_SMEM));
+        NAFP_CUDA(cudaFuncSetAttribute(ivfpq_code_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_CODE_SMEM));
+        ivfpq_assign_smem_kernel<<<static_cast<unsigned>(blocks), 256, ENC_ASSIGN_SMEM, ctx->stream>>>(idx->x32, row0, n, s->coarse,
+                                                                                                     s->nlist, s->assign);
+        ivfpq_code_smem_kernel<<<static_cast<unsigned>(blocks), 256, ENC_CODE_SMEM, ctx->stream>>>(idx->x32, row0, n, s->coarse, s->pq,
+                                                                                                 s->assign, s->codes);
+        ctx->launches++;
+    } else {
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        ivfpq_encode_kernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(idx->x32, row0, n, s->coarse, s->nlist, s->pq,
+                                                                                  s->m, s->dsub, s->assign, s->codes);
+    }
     ctx->launches++;
     if (s->refine) {
         ivfpqr_encode_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
