@@ -37,24 +37,26 @@ namespace nafp {
 
 constexpr int LM_ROWS = 128;              // list positions per tile (MMA N, accumulator columns)
 constexpr int LM_Q = 128;                 // query rows per work item (MMA M, TMEM lanes)
-constexpr int LM_KP = 32;                 // candidates kept per (query row, probed list): one warp-wide sorted list
+constexpr int LM_KP = 32;                 // entries of one warp-wide sorted candidate list
+constexpr int LM_GROUPS = 2;              // epilogue warp groups: each keeps its own list per query for its half of a tile's columns
+constexpr int LM_SLOT = LM_KP * LM_GROUPS; // candidates kept per (query row, probed list)
 constexpr int LM_MAX_K = 24;              // k the path answers (k + 8 spare candidates for the proof)
-constexpr int LM_MAX_NPROBE = 64;         // nprobe * LM_KP candidates are sorted by one block
+constexpr int LM_MAX_NPROBE = 64;         // nprobe * LM_SLOT candidates are sorted by one block
 constexpr int LM_STAGES = 2;
 constexpr int LM_HRING = 4;
 constexpr int LM_WAVES = 3;               // launches per search: probe rank 0 | ranks 1 .. LM_WAVE1_END-1 | the rest
 constexpr int LM_WAVE1_END = 4;
 constexpr int LM_PF = 6;                  // tiles ahead whose codes are prefetched into L2
-constexpr int LM_EPI_WARPS = 4, LM_DEC_WARPS = 8;
+constexpr int LM_EPI_WARPS = 4 * LM_GROUPS, LM_DEC_WARPS = 8;
 constexpr int LM_MMA_WARP = LM_EPI_WARPS + LM_DEC_WARPS;
-constexpr int LM_THREADS = (LM_MMA_WARP + 1) * 32;      // 416
+constexpr int LM_THREADS = (LM_MMA_WARP + 1) * 32;      // 544
 constexpr int LM_DEC_THREADS = LM_DEC_WARPS * 32;       // 256: (position, K block) per thread
 constexpr int LM_KB_BYTES = LM_ROWS * 128;              // 16 KB: one 64-dim K block of a tile (= of the query block)
-constexpr int LM_A_BYTES = 2 * LM_KB_BYTES;             // 32 KB
+constexpr int LM_TMEM_A = 256;                          // TMEM columns [256, 320): the item's query block (A operand), after the two accumulators
 constexpr int LM_B_BYTES = 2 * LM_KB_BYTES;             // 32 KB per stage
 constexpr int LM_TAB_BYTES = 64 * PQ_KSUB * 4;          // 64 KB: [sub-quantizer][code] -> two bf16
-constexpr int LM_LIST_BYTES = LM_Q * LM_KP * 8;         // 32 KB
-constexpr int LM_SMEM = 1024 + LM_A_BYTES + LM_STAGES * LM_B_BYTES + LM_TAB_BYTES + LM_LIST_BYTES + LM_HRING * LM_ROWS * 4 + 512;
+constexpr int LM_LIST_BYTES = LM_Q * LM_SLOT * 8;       // 64 KB
+constexpr int LM_SMEM = 1024 + LM_STAGES * LM_B_BYTES + LM_TAB_BYTES + LM_LIST_BYTES + LM_HRING * LM_ROWS * 4 + 512;
 constexpr int64_t LM_CHUNK_Q = 32768;     // query rows per launch group (bounds the candidate buffer: 256 B per pair)
 static_assert(LM_ROWS == 128, "the epilogue reads four 32-column chunks per tile");
 static_assert(LM_Q == LM_ROWS, "the query block and the tile share the K-block size");
@@ -77,7 +79,7 @@ struct LmState {
     float* qE = nullptr;                  // [nq] rounding bound of the bf16 scores
     float* dkA = nullptr;                 // [nq] k-th exact distance inside the nearest list
     int32_t* pairs = nullptr;             // [nq * nprobe] (query, probe) pairs grouped by (phase, list)
-    uint64_t* cand = nullptr;             // [nq * nprobe][LM_KP]
+    uint64_t* cand = nullptr;             // [nq * nprobe][LM_GROUPS][LM_KP]
     int64_t cap_pairs = 0, cap_q = 0;
     int32_t* hist = nullptr;              // [LM_WAVES * nlist] bucket sizes, the same of scatter cursors, [LM_WAVES] item counters
     LmItem* items = nullptr;
@@ -342,6 +344,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16: the A operand read from tensor memory (row = lane, 16 bf16 = 8 columns per K step)
+__device__ __forceinline__ void lm_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ float lm_key_score(uint64_t key) {
     return ord2f(static_cast<int32_t>(static_cast<uint32_t>(key >> 32) ^ 0x80000000u));
 }
@@ -354,10 +364,9 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                      uint64_t* __restrict__ cand) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a_s = smem;                                             // [kb 2][128 query rows][128 B]
-    uint8_t* b_s = a_s + LM_A_BYTES;                                 // [stage][kb 2][128 positions][128 B]
+    uint8_t* b_s = smem;                                             // [stage][kb 2][128 positions][128 B]
     uint32_t* tab_s = reinterpret_cast<uint32_t*>(b_s + LM_STAGES * LM_B_BYTES);
-    uint64_t* lst_s = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tab_s) + LM_TAB_BYTES);   // [128 queries][32] sorted, descending
+    uint64_t* lst_s = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tab_s) + LM_TAB_BYTES);   // [group][128 queries][32] sorted, descending
     float* h_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(lst_s) + LM_LIST_BYTES);            // [LM_HRING][128]
     LmBars* bars = reinterpret_cast<LmBars*>(h_s + LM_HRING * LM_ROWS);
 
@@ -379,7 +388,7 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
         mbar_fence_init();
     }
     if (warp == LM_MMA_WARP) {
-        tmem_alloc(&bars->tmem_base, 256);
+        tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -397,27 +406,30 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
         const LmItem item = items[it];
         const int lo = __ldg(loff + item.list);
         const int T = item.tiles;
-        // the item's query rows -> bf16, K-major, 128-byte swizzle (what TMA would have written); empty candidate lists
-        for (int task = threadIdx.x; task < LM_Q * 16; task += LM_THREADS) {
-            const int r = task >> 4, c16 = task & 15;
-            uint32_t o[4] = {0u, 0u, 0u, 0u};
-            if (r < item.len) {
-                const int qrow = __ldg(pairs + item.start + r) / nprobe;
-                const float4* src = reinterpret_cast<const float4*>(q + static_cast<int64_t>(qrow) * D128 + c16 * 8);
-                const float4 x = __ldg(src), y = __ldg(src + 1);
-                const __nv_bfloat162 b0 = __floats2bfloat162_rn(x.x, x.y), b1 = __floats2bfloat162_rn(x.z, x.w);
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(y.x, y.y), b3 = __floats2bfloat162_rn(y.z, y.w);
-                o[0] = *reinterpret_cast<const uint32_t*>(&b0);
-                o[1] = *reinterpret_cast<const uint32_t*>(&b1);
-                o[2] = *reinterpret_cast<const uint32_t*>(&b2);
-                o[3] = *reinterpret_cast<const uint32_t*>(&b3);
+        // The item's query rows -> bf16 -> TENSOR MEMORY (columns [LM_TMEM_A, + 64) of the query's lane): the A operand of
+        // every MMA of the item (no shared memory for it: the second set of candidate lists lives there instead).
+        if (warp < 4) {
+            const int r = warp * 32 + lane;
+            const float4* src = nullptr;
+            if (r < item.len) src = reinterpret_cast<const float4*>(q + static_cast<int64_t>(__ldg(pairs + item.start + r) / nprobe) * D128);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                      // 32 dims = 16 words per store
+                uint32_t v[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 x = src ? __ldg(src + c * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const __nv_bfloat162 b0 = __floats2bfloat162_rn(x.x, x.y), b1 = __floats2bfloat162_rn(x.z, x.w);
+                    v[2 * j] = *reinterpret_cast<const uint32_t*>(&b0);
+                    v[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&b1);
+                }
+                tmem_st_32x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + LM_TMEM_A + c * 16, v);
             }
-            const int kb = c16 >> 3, c = c16 & 7;
-            sts128(smem_u32(a_s) + kb * LM_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+            tc_wait_st();
+            tc_fence_before();
         }
-        for (int i = threadIdx.x; i < LM_Q * LM_KP; i += LM_THREADS) lst_s[i] = 0ull;
-        fence_proxy_async_smem();
+        for (int i = threadIdx.x; i < LM_Q * LM_SLOT; i += LM_THREADS) lst_s[i] = 0ull;
         __syncthreads();
+        tc_fence_after();
 
         if (warp >= LM_EPI_WARPS && warp < LM_MMA_WARP) {
             // ------------------------------------------------------------ decoders: codes -> bf16 tile
@@ -488,8 +500,7 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
         } else if (warp == LM_MMA_WARP) {
             // ------------------------------------------------------------ MMA issuer
             const uint32_t idesc = umma_idesc_f16(1u, 128u, static_cast<uint32_t>(LM_ROWS));
-            const uint64_t a_kb0 = umma_desc_sw128(smem_u32(a_s));
-            const uint64_t a_kb1 = a_kb0 + static_cast<uint64_t>(LM_KB_BYTES >> 4);
+            const uint32_t a_tmem = tmem_base + LM_TMEM_A;          // 16 bf16 = 8 columns per K step
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_s));
             for (int t = 0; t < T; ++t, ++g) {
                 const int s = g & 1;
@@ -502,9 +513,9 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                 const uint64_t b_kb1 = b_kb0 + static_cast<uint64_t>(LM_KB_BYTES >> 4);
                 if (mma_leader) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, a_kb0 + 2 * j, b_kb0 + 2 * j, idesc, j != 0 ? 1u : 0u);
+                    for (int j = 0; j < 4; ++j) lm_mma_ts(d_tmem, a_tmem + 8 * j, b_kb0 + 2 * j, idesc, j != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) tc_mma_f16(d_tmem, a_kb1 + 2 * j, b_kb1 + 2 * j, idesc, 1u);
+                    for (int j = 0; j < 4; ++j) lm_mma_ts(d_tmem, a_tmem + 32 + 8 * j, b_kb1 + 2 * j, idesc, 1u);
                     tc_commit(&bars->bempty[s]);
                     tc_commit(&bars->afull[s]);
                 }
@@ -512,7 +523,11 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
             }
         } else {
             // ------------------------------------------------------------ epilogue: one query per thread
-            const int ql = warp * 32 + lane;
+            // Warp e reads TMEM lane quadrant e & 3 (32 queries) and the 64 accumulator columns of half e >> 2 of every tile;
+            // each half keeps its own sorted list and threshold per query (two TMEM round trips per tile and warp instead
+            // of four: the epilogue, not the tensor pipe, sets the tile time).
+            const int qd = warp & 3, half = warp >> 2;
+            const int ql = qd * 32 + lane;
             const bool act = ql < item.len;
             const int pid = act ? __ldg(pairs + item.start + ql) : 0;
             float thr = INFINITY;                                       // padding lanes never fire
@@ -524,17 +539,17 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                     thr = 0.5f * (__ldg(gdist + pid) - __ldg(dkA + qrow)) - __ldg(qE + qrow);
                 }
             }
-            uint64_t* wl = lst_s + warp * 32 * LM_KP;
-            const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+            uint64_t* wl = lst_s + (half * LM_Q + qd * 32) * LM_KP;
+            const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + half * (LM_ROWS / 2);
             for (int t = 0; t < T; ++t, ++g) {
                 const int acc = g & 1;
                 mbar_wait_parked(&bars->afull[acc], (g >> 1) & 1);
                 mbar_wait_parked(&bars->hfull[g & (LM_HRING - 1)], (g >> 2) & 1);       // (already complete: the MMAs needed the same tile)
                 tc_fence_after();
-                const uint32_t hrow_u32 = smem_u32(h_s + (g & (LM_HRING - 1)) * LM_ROWS);
-                const uint32_t pos0 = static_cast<uint32_t>(lo + t * LM_ROWS);
+                const uint32_t hrow_u32 = smem_u32(h_s + (g & (LM_HRING - 1)) * LM_ROWS + half * (LM_ROWS / 2));
+                const uint32_t pos0 = static_cast<uint32_t>(lo + t * LM_ROWS + half * (LM_ROWS / 2));
 #pragma unroll 1
-                for (int c = 0; c < LM_ROWS / 32; ++c) {
+                for (int c = 0; c < LM_ROWS / 64; ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32(tlane + acc * LM_ROWS + c * 32, v);
                     tc_wait_ld();
@@ -593,18 +608,19 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
             }
         }
         __syncthreads();            // every accumulator of the item was consumed, every candidate list is final
-        if (warp < 4) {             // the item's candidate lists -> cand[pair][32]
-            const int ql = warp * 32 + lane;
+        if (warp < LM_EPI_WARPS) {  // the item's candidate lists -> cand[pair][group][32]
+            const int qd = warp & 3, half = warp >> 2;
+            const int ql = qd * 32 + lane;
             const int pid = ql < item.len ? __ldg(pairs + item.start + ql) : 0;
-            const uint64_t* wl = lst_s + warp * 32 * LM_KP;
+            const uint64_t* wl = lst_s + (half * LM_Q + qd * 32) * LM_KP;
             for (int qi = 0; qi < 32; ++qi) {
                 const int pq_id = __shfl_sync(0xffffffffu, pid, qi);
-                if (warp * 32 + qi < item.len) cand[static_cast<int64_t>(pq_id) * LM_KP + lane] = wl[qi * LM_KP + lane];
+                if (qd * 32 + qi < item.len) cand[static_cast<int64_t>(pq_id) * LM_SLOT + half * LM_KP + lane] = wl[qi * LM_KP + lane];
             }
         }
     }
     __syncthreads();
-    if (warp == LM_MMA_WARP) tmem_dealloc(tmem_base, 256);
+    if (warp == LM_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 // exact ADC distance of one list position for residual r = q - c_l, with ivfpq_scan_kernel's arithmetic: per
@@ -640,33 +656,49 @@ __device__ __forceinline__ float lm_exact_adc(const float* __restrict__ qs, cons
 // (probe ranks [0, pend), pend <= LM_WAVE1_END; +inf if they gave fewer than k) -- the next wave's threshold
 __global__ void ivfpq_lm_bound_kernel(const float* __restrict__ q, int64_t nq, int nprobe, int pend, int k,
                                       const uint64_t* __restrict__ cand, const int32_t* __restrict__ probes,
+                                      const float* __restrict__ gdist, const float* __restrict__ qE,
                                       const float* __restrict__ coarse, const float* __restrict__ pq,
                                       const uint8_t* __restrict__ lcodes, float* __restrict__ dkA) {
     __shared__ float qs[8][D128];
-    __shared__ float ds[8][LM_WAVE1_END * LM_KP];
+    __shared__ float ds[8][LM_WAVE1_END * LM_SLOT];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (i >= nq) return;
     reinterpret_cast<float4*>(qs[w])[lane] = reinterpret_cast<const float4*>(q + i * D128)[lane];
     __syncwarp();
-    for (int p = 0; p < pend; ++p) {
-        const uint64_t key = cand[(i * nprobe + p) * LM_KP + lane];
-        const int l = probes[i * nprobe + p];
+    const float dk_prev = dkA[i];          // the previous wave's bound (3.4e38 before the first): what cannot beat it is not re-scored
+    const float E = qE[i];
+    for (int p = 0; p < pend * LM_GROUPS; ++p) {               // (probe rank p / LM_GROUPS, list of epilogue group p % LM_GROUPS)
+        const uint64_t key = cand[(i * nprobe) * LM_SLOT + p * LM_KP + lane];
+        const int l = probes[i * nprobe + p / LM_GROUPS];
         float d = INFINITY;
-        if (key != 0ull && l >= 0)
+        // exact distance >= |q - c|^2 - 2 (bf16 score + E)
+        if (key != 0ull && l >= 0 && gdist[i * nprobe + p / LM_GROUPS] - 2.f * (lm_key_score(key) + E) <= dk_prev)
             d = lm_exact_adc(qs[w], coarse + static_cast<int64_t>(l) * D128, pq, lcodes, static_cast<uint32_t>(key));
         ds[w][p * LM_KP + lane] = d;
     }
     __syncwarp();
-    // rank of every distance (ties by position): the one of rank k - 1 is the bound
-    const int nv = pend * LM_KP;
-    for (int p = 0; p < pend; ++p) {
-        const int me = p * LM_KP + lane;
-        const float d = ds[w][me];
+    // compact the re-scored distances (most slots were skipped), then rank them: the one of rank k - 1 is the bound
+    int m = 0;
+    for (int p = 0; p < pend * LM_GROUPS; ++p) {
+        const float d = ds[w][p * LM_KP + lane];
+        const bool fin = d < INFINITY;
+        const unsigned mask = __ballot_sync(0xffffffffu, fin);
+        __syncwarp();
+        if (fin) ds[w][m + __popc(mask & ((1u << lane) - 1u))] = d;       // (target index <= source index: never an unread entry)
+        m += __popc(mask);
+        __syncwarp();
+    }
+    if (m < k) {
+        if (lane == 0) dkA[i] = INFINITY;
+        return;
+    }
+    for (int r = lane; r < m; r += 32) {
+        const float d = ds[w][r];
         int rank = 0;
-        for (int o = 0; o < nv; ++o) {
+        for (int o = 0; o < m; ++o) {
             const float od = ds[w][o];
-            rank += (od < d || (od == d && o < me)) ? 1 : 0;
+            rank += (od < d || (od == d && o < r)) ? 1 : 0;
         }
         if (rank == k - 1) dkA[i] = d;
     }
@@ -676,26 +708,29 @@ __global__ void ivfpq_lm_bound_kernel(const float* __restrict__ q, int64_t nq, i
 __global__ void __launch_bounds__(128)
 ivfpq_lm_merge_kernel(const float* __restrict__ q, int64_t q0, int nprobe, int k, const uint64_t* __restrict__ cand,
                       const int32_t* __restrict__ probes, const float* __restrict__ gdist, const float* __restrict__ qE,
-                      const float* __restrict__ coarse, const float* __restrict__ pq, const uint8_t* __restrict__ lcodes,
+                      const float* __restrict__ dkA, const float* __restrict__ coarse, const float* __restrict__ pq,
+                      const uint8_t* __restrict__ lcodes,
                       const int32_t* __restrict__ lids, int64_t label_offset, float* __restrict__ D, int64_t* __restrict__ I,
                       int32_t* __restrict__ redo_rows, int32_t* __restrict__ redo_count) {
     __shared__ float qs[D128];
-    __shared__ uint64_t keys[LM_MAX_NPROBE * LM_KP];
+    __shared__ uint64_t keys[LM_MAX_NPROBE * LM_SLOT];
     __shared__ int cnt_s, bound_s;
     const int64_t i = blockIdx.x;              // row inside the launch group
     const int tid = threadIdx.x;
     if (tid < 32) reinterpret_cast<float4*>(qs)[tid] = reinterpret_cast<const float4*>(q + i * D128)[tid];
     if (tid == 0) { cnt_s = 0; bound_s = INT_MAX; }
     __syncthreads();
-    const float E = qE[i];
-    const int total = nprobe * LM_KP;
+    const float E = qE[i], dk = dkA[i];
+    const int total = nprobe * LM_SLOT;
     // 1. gather: compact (probe rank, list position) of every survivor; lower bound on the distance of what the
     //    full lists dropped: g - 2 (score of the list's last entry + E)
     for (int e = tid; e < total; e += blockDim.x) {
         const uint64_t key = cand[i * total + e];
         if (key != 0ull) {
-            const int p = e / LM_KP;
-            keys[atomicAdd(&cnt_s, 1)] = (static_cast<uint64_t>(p) << 32) | static_cast<uint32_t>(key);
+            const int p = e / LM_SLOT;
+            // (a survivor whose distance cannot be below the last bound -- an upper bound of the k-th -- is not re-scored)
+            if (gdist[i * nprobe + p] - 2.f * (lm_key_score(key) + E) <= dk)
+                keys[atomicAdd(&cnt_s, 1)] = (static_cast<uint64_t>(p) << 32) | static_cast<uint32_t>(key);
             if ((e & (LM_KP - 1)) == LM_KP - 1)
                 atomicMin(&bound_s, f2ord(gdist[i * nprobe + p] - 2.f * (lm_key_score(key) + E)));
         }
@@ -754,7 +789,7 @@ static int lm_reserve(nafp_index* idx, int64_t nc, int nprobe) {
         NAFP_CUDA(cudaMalloc(&L->probes, static_cast<size_t>(cp) * sizeof(int32_t)));
         NAFP_CUDA(cudaMalloc(&L->gdist, static_cast<size_t>(cp) * sizeof(float)));
         NAFP_CUDA(cudaMalloc(&L->pairs, static_cast<size_t>(cp) * sizeof(int32_t)));
-        NAFP_CUDA(cudaMalloc(&L->cand, static_cast<size_t>(cp) * LM_KP * sizeof(uint64_t)));
+        NAFP_CUDA(cudaMalloc(&L->cand, static_cast<size_t>(cp) * LM_SLOT * sizeof(uint64_t)));
         NAFP_CUDA(cudaMalloc(&L->qE, static_cast<size_t>(cq) * sizeof(float)));
         NAFP_CUDA(cudaMalloc(&L->dkA, static_cast<size_t>(cq) * sizeof(float)));
         L->cap_q = cq;
@@ -828,7 +863,7 @@ int ivfpq_search_lm(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
         NAFP_CUDA(cudaMemcpyAsync(cursor, cur.data(), nb * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         NAFP_CUDA(cudaMemsetAsync(counters, 0, LM_WAVES * sizeof(int32_t), ctx->stream));
         lm_scatter_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, ctx->stream>>>(L->probes, np, nprobe, nlist, cursor, L->pairs);
-        NAFP_CUDA(cudaMemsetAsync(L->cand, 0, static_cast<size_t>(np) * LM_KP * sizeof(uint64_t), ctx->stream));
+        NAFP_CUDA(cudaMemsetAsync(L->cand, 0, static_cast<size_t>(np) * LM_SLOT * sizeof(uint64_t), ctx->stream));
         NAFP_CUDA(cudaMemsetAsync(L->dkA, 0x7f, static_cast<size_t>(nc) * sizeof(float), ctx->stream));     // 0x7f7f7f7f = 3.4e38: "no bound"
         ctx->launches += 3;
         for (int wv = 0; wv < LM_WAVES; ++wv) {
@@ -846,11 +881,11 @@ int ivfpq_search_lm(nafp_index* idx, const float* q_dev, int64_t nq, int k, floa
             if (later) {               // the bound the later waves' thresholds are built from
                 const int pend = std::min(wv == 0 ? 1 : LM_WAVE1_END, nprobe);
                 ivfpq_lm_bound_kernel<<<static_cast<unsigned>((nc + 7) / 8), 256, 0, ctx->stream>>>(
-                    qp, nc, nprobe, pend, k, L->cand, L->probes, s->coarse, s->pq, s->lcodes, L->dkA);
+                    qp, nc, nprobe, pend, k, L->cand, L->probes, L->gdist, L->qE, s->coarse, s->pq, s->lcodes, L->dkA);
                 ctx->launches++;
             }
         }
-        ivfpq_lm_merge_kernel<<<static_cast<unsigned>(nc), 128, 0, ctx->stream>>>(qp, q0, nprobe, k, L->cand, L->probes, L->gdist, L->qE,
+        ivfpq_lm_merge_kernel<<<static_cast<unsigned>(nc), 128, 0, ctx->stream>>>(qp, q0, nprobe, k, L->cand, L->probes, L->gdist, L->qE, L->dkA,
                                                                                  s->coarse, s->pq, s->lcodes, s->lids, idx->label_offset,
                                                                                  D_dev + q0 * k, I_dev + q0 * k, s->redo_rows, redo_count);
         ctx->launches++;
