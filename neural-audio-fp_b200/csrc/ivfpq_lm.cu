@@ -13,14 +13,17 @@
 //                   64 sub-vectors up in a bf16 copy of the PQ codebooks kept in shared memory (64 KB, one bank per
 //                   sub-quantizer: conflict-free) and write them as a 128 x 128 bf16 K-major SWIZZLE_128B tile -- the
 //                   layout TMA would have produced from a decoded copy of the rows -- into a 2-stage ring
-//   MMA warp        tcgen05.mma  D[query][position] = Q (128 x 128 bf16, gathered once per item) x tile^T, fp32
-//                   accumulators double-buffered in TMEM
-//   epilogue warps  one query per thread: s = D - h against the query's threshold (one register); the rare hits are
-//                   inserted warp-cooperatively into the query's sorted 32-entry candidate list in shared memory
+//   MMA warp        tcgen05.mma  D[query][position] = Q (128 x 128 bf16, written to TENSOR MEMORY once per item) x tile^T
+//                   - h: the row term rides a ninth K step -- the decoders write -h as three bf16 (hi + mid + lo, 24 bits)
+//                   into a third K block of the stage, the query block has three columns of ones --; fp32 accumulators
+//                   double-buffered in TMEM
+//   epilogue warps  two groups of four, one query per thread, 64 of the tile's columns per group: the accumulator IS the
+//                   score; it is compared with the query's threshold (one register); the rare hits are inserted
+//                   warp-cooperatively into the group's sorted 32-entry candidate list of the query in shared memory
 //
-// Two launches per search.  Phase A scans every query's NEAREST list with an open threshold; the exact fp32 ADC
-// distance of its k-th candidate bounds the answer (Dk_A).  Phase B scans the other nprobe - 1 lists with the
-// threshold  0.5 (|q - c_l|^2 - Dk_A) - E  (E = the bf16 rounding bound |q| max|d| 2^-8): rows below it cannot
+// Three launches per search.  Wave 0 scans every query's NEAREST list with an open threshold; the exact fp32 ADC
+// distance of its k-th candidate bounds the answer (Dk).  Waves 1 (probe ranks 1-3) and 2 (the rest) start from the
+// threshold  0.5 (|q - c_l|^2 - Dk) - E  (E = the bf16 rounding bound |q| max|d| 2^-8): rows below it cannot
 // enter the top k, so almost nothing is inserted.  ivfpq_lm_merge_kernel re-scores the survivors with the LUT
 // kernel's own fp32 arithmetic, sorts, and PROVES the answer (a full 32-entry list must end below the k-th exact
 // distance by more than the rounding bound); unproven rows -- duplicates, ties -- go to the LUT kernel.
@@ -43,7 +46,6 @@ constexpr int LM_SLOT = LM_KP * LM_GROUPS; // candidates kept per (query row, pr
 constexpr int LM_MAX_K = 24;              // k the path answers (k + 8 spare candidates for the proof)
 constexpr int LM_MAX_NPROBE = 64;         // nprobe * LM_SLOT candidates are sorted by one block
 constexpr int LM_STAGES = 2;
-constexpr int LM_HRING = 4;
 constexpr int LM_WAVES = 3;               // launches per search: probe rank 0 | ranks 1 .. LM_WAVE1_END-1 | the rest
 constexpr int LM_WAVE1_END = 4;
 constexpr int LM_PF = 6;                  // tiles ahead whose codes are prefetched into L2
@@ -53,10 +55,10 @@ constexpr int LM_THREADS = (LM_MMA_WARP + 1) * 32;      // 544
 constexpr int LM_DEC_THREADS = LM_DEC_WARPS * 32;       // 256: (position, K block) per thread
 constexpr int LM_KB_BYTES = LM_ROWS * 128;              // 16 KB: one 64-dim K block of a tile (= of the query block)
 constexpr int LM_TMEM_A = 256;                          // TMEM columns [256, 320): the item's query block (A operand), after the two accumulators
-constexpr int LM_B_BYTES = 2 * LM_KB_BYTES;             // 32 KB per stage
+constexpr int LM_B_BYTES = 3 * LM_KB_BYTES;             // 48 KB per stage: two K blocks of decoded rows + the K block of -h
 constexpr int LM_TAB_BYTES = 64 * PQ_KSUB * 4;          // 64 KB: [sub-quantizer][code] -> two bf16
 constexpr int LM_LIST_BYTES = LM_Q * LM_SLOT * 8;       // 64 KB
-constexpr int LM_SMEM = 1024 + LM_STAGES * LM_B_BYTES + LM_TAB_BYTES + LM_LIST_BYTES + LM_HRING * LM_ROWS * 4 + 512;
+constexpr int LM_SMEM = 1024 + LM_STAGES * LM_B_BYTES + LM_TAB_BYTES + LM_LIST_BYTES + 512;
 constexpr int64_t LM_CHUNK_Q = 32768;     // query rows per launch group (bounds the candidate buffer: 256 B per pair)
 static_assert(LM_ROWS == 128, "the epilogue reads four 32-column chunks per tile");
 static_assert(LM_Q == LM_ROWS, "the query block and the tile share the K-block size");
@@ -331,7 +333,6 @@ struct LmBars {
     uint64_t bempty[LM_STAGES];
     uint64_t afull[2];
     uint64_t aempty[2];
-    uint64_t hfull[LM_HRING];      // h_s slot written (4 decoder warps): the decoders' direct hand-off to the epilogue
     uint32_t tmem_base;
     int item;
 };
@@ -367,14 +368,18 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
     uint8_t* b_s = smem;                                             // [stage][kb 2][128 positions][128 B]
     uint32_t* tab_s = reinterpret_cast<uint32_t*>(b_s + LM_STAGES * LM_B_BYTES);
     uint64_t* lst_s = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tab_s) + LM_TAB_BYTES);   // [group][128 queries][32] sorted, descending
-    float* h_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(lst_s) + LM_LIST_BYTES);            // [LM_HRING][128]
-    LmBars* bars = reinterpret_cast<LmBars*>(h_s + LM_HRING * LM_ROWS);
+    LmBars* bars = reinterpret_cast<LmBars*>(reinterpret_cast<uint8_t*>(lst_s) + LM_LIST_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < LM_TAB_BYTES / 16; i += LM_THREADS)
         reinterpret_cast<uint4*>(tab_s)[i] = __ldg(reinterpret_cast<const uint4*>(tab) + i);
+    // the third K block of every stage carries -h of the tile's rows in its first three bf16 columns (below); the rest of
+    // it stays zero for the life of the kernel
+    for (int st = 0; st < LM_STAGES; ++st)
+        for (int i = threadIdx.x; i < LM_KB_BYTES / 16; i += LM_THREADS)
+            reinterpret_cast<uint4*>(b_s + st * LM_B_BYTES + 2 * LM_KB_BYTES)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) {
         for (int s = 0; s < LM_STAGES; ++s) {
             mbar_init(&bars->bfull[s], LM_DEC_WARPS);
@@ -384,7 +389,6 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
             mbar_init(&bars->afull[a], 1);
             mbar_init(&bars->aempty[a], LM_EPI_WARPS);
         }
-        for (int a = 0; a < LM_HRING; ++a) mbar_init(&bars->hfull[a], LM_ROWS / 32);
         mbar_fence_init();
     }
     if (warp == LM_MMA_WARP) {
@@ -396,6 +400,17 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
     const bool mma_leader = warp == LM_MMA_WARP ? elect_one() : false;
+    if (warp < 4) {             // the A columns that pick -h out of the third K block: (1, 1, 1, 0, ...) in bf16, every query lane
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+        v[0] = 0x3F803F80u;     // bf16 (1.0, 1.0)
+        v[1] = 0x00003F80u;     // bf16 (1.0, 0.0)
+        tmem_st_32x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + LM_TMEM_A + 64, v);
+        tc_wait_st();
+        tc_fence_before();
+    }
+    fence_proxy_async_smem();   // (the zeroed K blocks)
 
     uint32_t g = 0;                 // tiles this CTA has gone through (every role counts the same sequence)
     for (;;) {
@@ -487,13 +502,23 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                         const uint32_t row = static_cast<uint32_t>(4 * (rg0 + 4 * j) + b);
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + row * 128 + ((chunk ^ (row & 7u)) << 4)), "r"(v[4 * j + b]) : "memory");
                     }
-                if (dt < LM_ROWS) h_s[(g & (LM_HRING - 1)) * LM_ROWS + dt] = hv;
+                if (dt < LM_ROWS) {
+                    // -h = hi + mid + lo in bf16 (24 significant bits): the MMA adds it to q . d through three columns of ones
+                    uint32_t w0 = 0x0000FF80u, w1 = 0u;                            // h = +inf (padding, halo): -inf, 0, 0
+                    if (hv < INFINITY) {
+                        const float nhv = -hv;
+                        const __nv_bfloat16 b_hi = __float2bfloat16_rn(nhv);
+                        const float r1 = nhv - __bfloat162float(b_hi);
+                        const __nv_bfloat16 b_mid = __float2bfloat16_rn(r1);
+                        const __nv_bfloat16 b_lo = __float2bfloat16_rn(r1 - __bfloat162float(b_mid));
+                        w0 = static_cast<uint32_t>(__bfloat16_as_ushort(b_hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b_mid)) << 16);
+                        w1 = static_cast<uint32_t>(__bfloat16_as_ushort(b_lo));
+                    }
+                    sts128(smem_u32(b_s) + s * LM_B_BYTES + 2 * LM_KB_BYTES + dt * 128 + ((dt & 7) << 4), w0, w1, 0u, 0u);
+                }
                 fence_proxy_async_smem();          // this thread's tile bytes -> visible to the tensor core's (async) proxy
                 __syncwarp();
                 if (lane == 0) {
-                    // (slot g & 3 is written again for tile g + 4, whose stage is free only after tile g + 2's MMAs, which wait
-                    // for the epilogue of tile g: never more than one phase ahead of the reader)
-                    if (dt < LM_ROWS) mbar_arrive(&bars->hfull[g & (LM_HRING - 1)]);
                     mbar_arrive(&bars->bfull[s]);
                 }
             }
@@ -516,6 +541,7 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
                     for (int j = 0; j < 4; ++j) lm_mma_ts(d_tmem, a_tmem + 8 * j, b_kb0 + 2 * j, idesc, j != 0 ? 1u : 0u);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) lm_mma_ts(d_tmem, a_tmem + 32 + 8 * j, b_kb1 + 2 * j, idesc, 1u);
+                    lm_mma_ts(d_tmem, a_tmem + 64, b_kb1 + static_cast<uint64_t>(LM_KB_BYTES >> 4), idesc, 1u);       // ... - h
                     tc_commit(&bars->bempty[s]);
                     tc_commit(&bars->afull[s]);
                 }
@@ -544,26 +570,16 @@ ivfpq_lm_scan_kernel(const float* __restrict__ q, int nprobe, const LmItem* __re
             for (int t = 0; t < T; ++t, ++g) {
                 const int acc = g & 1;
                 mbar_wait_parked(&bars->afull[acc], (g >> 1) & 1);
-                mbar_wait_parked(&bars->hfull[g & (LM_HRING - 1)], (g >> 2) & 1);       // (already complete: the MMAs needed the same tile)
                 tc_fence_after();
-                const uint32_t hrow_u32 = smem_u32(h_s + (g & (LM_HRING - 1)) * LM_ROWS + half * (LM_ROWS / 2));
                 const uint32_t pos0 = static_cast<uint32_t>(lo + t * LM_ROWS + half * (LM_ROWS / 2));
 #pragma unroll 1
                 for (int c = 0; c < LM_ROWS / 64; ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32(tlane + acc * LM_ROWS + c * 32, v);
                     tc_wait_ld();
-                    float sc[32];
+                    float sc[32];                  // q . d - h: the accumulator already holds the score
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 hh;                                                       // broadcast read (explicit LDS.128)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(hh.x), "=f"(hh.y), "=f"(hh.z), "=f"(hh.w)
-                                     : "r"(hrow_u32 + (c * 32 + 4 * j4) * 4));
-                        sc[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) - hh.x;
-                        sc[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) - hh.y;
-                        sc[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) - hh.z;
-                        sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) - hh.w;
-                    }
+                    for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]);
                     // one vote per chunk on the hot path (vote -> branch latency was half of the epilogue's time with one per
                     // 8 columns); the per-group votes run only inside the rare branch
                     float mg[4];
