@@ -103,3 +103,43 @@ def test_ivfpqr_refinement_improves_the_ranking():
     # the refined list is a re-ordering of (a subset of) the 4k first-level candidates
     _, I4 = IVFPQ.search(rr, query[:60], 80)
     assert all(set(I[r]) <= set(I4[r]) for r in range(60))
+
+
+def test_list_major_formulation_and_its_rounding_bound():
+    """The algebra and the error bound csrc/ivfpq_lm.cu rests on, on the oracle's own quantities: with xhat = c_l + d
+    (d = the decoded PQ residual), |q - xhat|^2 = |q - c_l|^2 - 2 (q . d - h) with h = 0.5 |d|^2 + c_l . d, and the score the
+    tensor cores compute from bf16-rounded q and d differs from the exact q . d by at most E = |q| max|d| 2^-8 * 1.03 -- the
+    slack the thresholds and the proof of the CUDA path subtract.  Also: -h split into three bf16 pieces (how the kernel
+    feeds it to the MMA) reproduces h to fp32 accuracy."""
+    import torch
+    from oracle.ivfpq_index import IVFPQ
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((6000, 128)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    o = IVFPQ(128, 32, 64, 8)
+    o.train(x[:4000], seed=3)
+    o.add(x)
+    q = x[:64] + 0.3 * rng.standard_normal((64, 128)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    rows = np.arange(0, 6000, 7)
+    d = o.pq[np.arange(64)[None, :], o.codes[rows]].reshape(len(rows), 128).astype(np.float64)      # decoded residuals
+    c = o.coarse[o.assign[rows]].astype(np.float64)
+    xhat = c + d
+    np.testing.assert_allclose(xhat, o.reconstruct(rows), atol=1e-6)
+    h = 0.5 * (d * d).sum(1) + (c * d).sum(1)
+    q64 = q.astype(np.float64)
+    lhs = ((q64[:, None, :] - xhat[None, :, :]) ** 2).sum(2)
+    g = ((q64[:, None, :] - c[None, :, :]) ** 2).sum(2)
+    rhs = g - 2.0 * (q64 @ d.T - h[None, :])
+    np.testing.assert_allclose(lhs, rhs, atol=1e-10)
+    # bf16 operands, exact accumulation: the worst case of what the MMA adds up
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).to(torch.float64).numpy()
+    err = np.abs(bf(q) @ bf(d).T - q64 @ d.T)
+    E = np.linalg.norm(q64, axis=1)[:, None] * np.sqrt((d * d).sum(1).max()) * (1.03 / 256.0)
+    assert (err <= E).all() and err.max() > 0.02 * E.min()          # a real bound, not a vacuous one
+    # -h = hi + mid + lo in bf16
+    nh = (-h).astype(np.float32)
+    hi = bf(nh)
+    mid = bf((nh - hi).astype(np.float32))
+    lo = bf((nh - hi - mid).astype(np.float32))
+    assert np.abs((hi + mid + lo) - nh.astype(np.float64)).max() <= 2.0 ** -22 * np.abs(nh).max()
